@@ -1,0 +1,211 @@
+/*
+ * pka_b200.h -- C ABI of libpka_b200.so, the sm_100a kernel library under the Python mirror of
+ * boji123/pytorch-kaldi-asr's acoustic-model hot path.
+ *
+ * The reference has no FFI of its own: its "kernel layer" is stock ATen called from Python modules.  Each entry
+ * point below therefore names the reference *op sequence* (file:line under /root/reference) it replaces.
+ *   T/ = project/attention-transformer-timit/local/pytorch/transformer/
+ *   L/ = project/attention-transformer-timit/local/      U/ = pytorch/utils/
+ *
+ * Contract (all entry points)
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - the caller (PyTorch) owns every buffer; the library never allocates, frees or keeps a pointer.
+ *   - all work is enqueued on `stream`; no host synchronisation; CUDA-graph capturable.
+ *   - return 0 on success, a PKA_E* code otherwise; pka_last_error() gives a thread-local message.
+ *   - `dtype`: element type of activations in HBM (PKA_F32 / PKA_BF16); parameters and statistics are fp32.
+ *   - dropout: keep-mask bit of element `i` at `site` in training step `*step_ptr` is a pure function
+ *     philox4x32-10(seed, site, step, i) so the backward pass regenerates it instead of storing it;
+ *     p == 0 disables it.  pka_dropout_mask() materialises the same bits for tests.
+ */
+#ifndef PKA_B200_H
+#define PKA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PKA_F32 = 0, PKA_BF16 = 1 };
+enum {
+  PKA_OK = 0,
+  PKA_EINVAL = 1,      /* bad shape / argument                      */
+  PKA_EUNSUPPORTED = 2,/* dimension or dtype outside what is built  */
+  PKA_EALIGN = 3,      /* pointer or leading dimension misaligned   */
+  PKA_ELAUNCH = 4,     /* cudaGetLastError() after launch           */
+  PKA_EDEVICE = 5      /* not an sm_100 device / driver entry point missing */
+};
+
+#define PKA_MAX_CTX 8
+
+typedef struct {
+  float p;                         /* drop probability; 0 = off */
+  uint32_t site;                   /* dropout site id (one per nn.Dropout call site of the reference) */
+  uint64_t seed;
+  const uint64_t* step_ptr;        /* device counter, advanced once per training step (may be NULL = 0) */
+} pka_dropout;
+
+const char* pka_last_error(void);
+int pka_version(void);
+/* number of kernels this library has launched so far in this process (one per successful launch call) */
+uint64_t pka_launch_count(void);
+/* 0 if the current device is compute capability 10.x, PKA_EDEVICE otherwise */
+int pka_check_device(void);
+
+/* ---- (a) front-end: [optional per-utterance CMVN] -> frame folding -> frame splicing --------------------------
+ * replaces: Kaldi `apply-cmvn` (P/run.sh:37-42) + fold_seq_and_mask (T/Models.py:51-65) + ConcatLayer
+ * (L/pytorch/TDNN.py:20-28).  feats f32[B,T,F] zero padded; lengths[B] (only read when cmvn_mode != 0);
+ * out[B, T/fold, n_ctx*F*fold]; zero rows are spliced in beyond the *tensor* edges exactly like ConcatLayer.
+ * cmvn_mode: 0 none, 1 mean, 2 mean+variance.  stats_ws: float[B*2*F] scratch (cmvn only). */
+int pka_frontend_fwd(const float* feats, const int32_t* lengths, void* out, int out_dtype, int B, int T, int F,
+                     int fold, const int32_t* ctx_host, int n_ctx, int cmvn_mode, float* stats_ws, void* stream);
+
+/* ---- (c) GEMM family, fp32 SIMT "exact" path -------------------------------------------------------------------
+ * C[M,N] (+)= epilogue( sum_{s<nseg} sum_{k<K} A_s(m,k) * B_s(k,n) ), batched over `nbatch` (grid.z).
+ *   transA=0: A_s(m,k) = A[(m+shiftA[s])*lda + s*a_seg_off + k]; rows are (utterance, frame) pairs with T frames per
+ *             utterance, a shifted row that leaves [0,T) reads as 0  -> implicit ConcatLayer, never materialised.
+ *   transA=1: A(m,k)   = A[k*lda + m]                               (weight-gradient: reduction over frames)
+ *   transB=1: B_s(k,n) = B[n*ldb + s*b_seg_off + k]                 (nn.Linear weight [out,in])
+ *   transB=0: B_s(k,n) = B[(k+shiftB[batch])*ldb + s*b_seg_off + n] (frame shift on the reduction index, same T rule)
+ * epilogue: + bias[n], ReLU, dropout, + residual[m*ldr+n], accumulate into C.
+ * replaces: BottleLinear (T/Modules.py:8-30), TDNNLayer cat+Linear+ReLU+dropout (L/pytorch/TDNN.py:41-46),
+ * LDALayer (:53-55), per-head bmm projections (T/SubLayers.py:49-56), Conv1d k=1 FFN (T/SubLayers.py:81-83), and
+ * their autograd backward. */
+typedef struct {
+  const void* A; const void* B; void* C;
+  const float* bias; const void* residual;
+  int32_t M, N, K, nseg, nbatch;
+  int32_t lda, ldb, ldc, ldr;
+  int32_t transA, transB;
+  int64_t a_seg_off, b_seg_off;
+  int64_t a_batch_off, b_batch_off, c_batch_off;
+  int32_t shiftA[PKA_MAX_CTX];
+  int32_t shiftB[PKA_MAX_CTX];
+  int32_t T;
+  int32_t relu;
+  int32_t accumulate;
+  int32_t reserved;
+  pka_dropout drop;
+} pka_gemm_desc;
+int pka_gemm_f32(const pka_gemm_desc* d, void* stream);
+
+/* ---- (c) GEMM family, bf16 tcgen05/TMEM/TMA path ---------------------------------------------------------------
+ * Same contract, restricted to what the tensor-core tiles support: A bf16 [rows, K] row-major (optionally a
+ * [B,T,K] view with per-segment frame shifts done by 3-D TMA out-of-bounds zero fill), B bf16 [N, nseg*K] row-major
+ * ("weight" layout, transB=1), fp32 accumulation in TMEM, epilogue bias/ReLU/dropout/residual, C bf16 or fp32.
+ * tmap_ws: 3*128 bytes of *host* scratch for the CUtensorMap objects (passed as __grid_constant__). */
+int pka_gemm_bf16_tc(const pka_gemm_desc* d, int c_dtype, void* stream);
+
+/* ---- (b) attention ----------------------------------------------------------------------------------------------
+ * replaces: ScaledDotProductAttention.forward (T/Modules.py:75-97) with the masks of T/Models.py:27-49 evaluated
+ * in-kernel.  q[B,Lq,ldq] k[B,Lk,ldk] v[B,Lk,ldv]: head h lives in columns [h*dk,(h+1)*dk).  key_mask u8[B,Lk]
+ * (1 = real).  Allowed pairs: key real AND (no band OR i+band_start <= j <= i+band_end).  Rows without an allowed
+ * key give 0 output and 0 gradient.  lse f32[B,H,Lq] (log-sum-exp of scaled scores; -inf for dead rows).
+ * probs_out (optional, f32[B,H,Lq,Lk]) materialises the post-softmax, pre-dropout probabilities the reference
+ * returns as `attn`. */
+typedef struct {
+  int32_t B, H, Lq, Lk, dk, dv;
+  int32_t ldq, ldk, ldv, ldo;
+  int32_t use_band, band_start, band_end;
+  float scale;
+  pka_dropout drop;
+} pka_attn_desc;
+int pka_attn_fwd(const pka_attn_desc* d, int dtype, const void* q, const void* k, const void* v,
+                 const uint8_t* key_mask, void* out, float* lse, float* probs_out, void* stream);
+/* dq/dk/dv use the same leading dimensions as q/k/v. delta_ws: float[B*H*Lq] scratch. */
+int pka_attn_bwd(const pka_attn_desc* d, int dtype, const void* q, const void* k, const void* v,
+                 const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* delta_ws,
+                 void* dq, void* dk, void* dv, void* stream);
+
+/* ---- (c) fused [dropout] + residual add + LayerNormalization ----------------------------------------------------
+ * replaces: `layer_norm(dropout(x) + residual)` (T/SubLayers.py:65-68,85-86) with LayerNormalization of
+ * T/Modules.py:42-51: y = (z-mean)/(std_unbiased+eps)*a + b.  The "identity when size(1)==1" rule is applied by the
+ * caller (it is a shape rule).  mean/rinv f32[rows] are saved for backward (rinv = 1/(std+eps)). */
+int pka_add_layernorm_fwd(const void* x, const void* residual, const float* a, const float* b, void* y, float* mean,
+                          float* rinv, int dtype, int rows, int D, float eps, const pka_dropout* drop, void* stream);
+/* dres always written; dx written only when drop->p > 0 (otherwise dx == dres and may be NULL).
+ * dab_ws: float[2*D*pka_ln_bwd_blocks(rows)] scratch; da/db are *accumulated into* (+=). */
+int pka_ln_bwd_blocks(int rows);
+int pka_add_layernorm_bwd(const void* dy, const void* x, const void* residual, const float* a, const float* mean,
+                          const float* rinv, void* dx, void* dres, float* da, float* db, float* dab_ws, int dtype,
+                          int rows, int D, float eps, const pka_dropout* drop, void* stream);
+
+/* ---- (d) summed cross-entropy with PAD mask, optional label smoothing, fused argmax accuracy -------------------
+ * replaces: cal_loss / get_performance (L/train.py:58-90).  logits[N,V] (ld = V), goal i64[N], PAD = 0 ignored.
+ * out3: float[3] = {loss_sum, n_correct, n_words}; lse f32[N] saved for backward; part_ws float[3*pka_ce_blocks(N)]. */
+int pka_ce_blocks(int N);
+int pka_ce_fwd(const void* logits, const int64_t* goal, int dtype, int N, int V, int smoothing, float eps,
+               float* out3, float* lse, float* part_ws, void* stream);
+/* dlogits = grad_out[0] * (softmax - target) on non-PAD rows, 0 on PAD rows. */
+int pka_ce_bwd(const void* logits, const int64_t* goal, const float* lse, const float* grad_out, void* dlogits,
+               int dtype, int N, int V, int smoothing, float eps, void* stream);
+
+/* ---- element-wise pieces of the path ----------------------------------------------------------------------------
+ * out[b,l,:] = dropout(emb[tok[b,l],:] + pos[l,:])           (T/Models.py:195-213) */
+int pka_embed_pos_fwd(const int64_t* tok, const float* emb, const float* pos, void* out, int dtype, int B, int L,
+                      int D, int V, const pka_dropout* drop, void* stream);
+/* demb[v,:] += sum over (b,l) with tok==v of dropout_bwd(dout[b,l,:]); row `padding_idx` is left untouched.
+ * Deterministic (one CTA per vocabulary row, fixed summation order). */
+int pka_embed_bwd(const int64_t* tok, const void* dout, float* demb, int dtype, int B, int L, int D, int V,
+                  int padding_idx, const pka_dropout* drop, void* stream);
+/* out[r,:] = dropout(x[r,:] + rowvec[(r % period),:])  (rowvec may be NULL)   (T/Models.py:164-165,226) */
+int pka_add_rowvec_dropout_fwd(const void* x, const float* rowvec, void* out, int dtype, int64_t rows, int D,
+                               int period, const pka_dropout* drop, void* stream);
+/* dx = keep * dy / (1-p) */
+int pka_dropout_bwd(const void* dy, void* dx, int dtype, int64_t n, const pka_dropout* drop, void* stream);
+/* dz = (y > 0) ? dy * scale : 0  -- backward of ReLU followed by dropout, using only the layer output y
+ * (y > 0  <=>  pre-activation > 0 and kept).  scale = 1/(1-p). */
+int pka_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float scale, void* stream);
+/* out[n] (+)= sum_r x[r*ld + n]; part_ws float[pka_colsum_chunks(rows)*N]; deterministic two-stage reduction */
+int pka_colsum_chunks(int64_t rows);
+int pka_colsum(const void* x, float* out, float* part_ws, int dtype, int64_t rows, int N, int ld, int accumulate,
+               void* stream);
+/* keep[i] = 1/0 for i < n : the bits every kernel above derives for (seed, site, *step_ptr) */
+int pka_dropout_mask(uint8_t* keep, int64_t n, const pka_dropout* drop, void* stream);
+int pka_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* dst[c, r] = src[r, c] for a [rows, cols] matrix (dtype conversion allowed) */
+int pka_transpose(const void* src, int src_dtype, void* dst, int dst_dtype, int rows, int cols, void* stream);
+
+/* ---- optimiser ---------------------------------------------------------------------------------------------------
+ * replaces: torch.optim.Adam.step over 72 tensors + ScheduledOptim.update_learning_rate (T/Optim.py:13-27,
+ * L/train.py:376-380) with one launch over the flat parameter arena.
+ * state: int64[2] = {adam_t, n_current_steps}; lr: float[1] on device.  pka_adam_step uses t = adam_t+1 and then
+ * stores it; pka_lr_tick does n+=1; lr = start_lr*c/(n+c).  bf16_shadow (optional) receives the updated weights
+ * rounded to bf16 for the tensor-core path.  If grad_scale_inv != NULL gradients are multiplied by it first. */
+int pka_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                  float lr_host, int64_t* state, float beta1, float beta2, float eps, void* bf16_shadow,
+                  void* stream);
+int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream);
+int pka_counter_inc(uint64_t* counter, void* stream);
+
+/* ---- (e) beam-search decoding ------------------------------------------------------------------------------------
+ * replaces: the per-step body of translate_batch (L/decode.py:54-98) + Lattice.advance (T/Lattice.py:35-81).
+ * See pytorch-kaldi-asr_b200/decode.py for the device-resident lattice layout these operate on. */
+typedef struct {
+  int32_t n_utt, beam, V, max_edges, max_len;
+  int32_t eos, force_full_length;
+} pka_beam_desc;
+/* log-softmax over V of logits[n_utt*beam, V] (fp32), candidate scores in fp64 = parent weight + log-prob, finished
+ * hypotheses appended, warp-level top-`beam` with lowest-flat-index tie rule, lattice arrays updated in place. */
+int pka_beam_advance(const pka_beam_desc* d, const float* logits, int32_t* edge_prev, int32_t* edge_word,
+                     double* edge_weight, int32_t* n_edges, int32_t* beam_edges, int32_t* beam_count,
+                     int32_t* slot_edge, int32_t* slot_active, int32_t* curr_length, int32_t* done,
+                     int32_t* n_not_done, void* stream);
+/* tree attention over the lattice: the query of slot s (edge e) attends to e and its <= (-band_start) ancestors.
+ * kcache/vcache f32[n_utt, max_edges, H*dk] hold the keys/values written when each edge was the newest token. */
+int pka_tree_attn(const float* q, const float* kcache, const float* vcache, const int32_t* edge_prev,
+                  const int32_t* slot_edge, const int32_t* slot_active, float* out, int n_utt, int beam, int max_edges,
+                  int H, int dk, int ldq, int window, float scale, void* stream);
+/* scatter the new token's K/V rows (slot-major [n_utt*beam, ld]) into the per-edge caches */
+int pka_kv_append(const float* k_new, const float* v_new, int ld, float* kcache, float* vcache,
+                  const int32_t* slot_edge, const int32_t* slot_active, int n_utt, int beam, int max_edges, int HD,
+                  void* stream);
+/* decoder input of every slot: emb[word(edge)] + pos[depth(edge)] */
+int pka_beam_embed(const float* emb, const float* pos, const int32_t* edge_word, const int32_t* edge_depth,
+                   const int32_t* slot_edge, const int32_t* slot_active, float* out, int n_utt, int beam,
+                   int max_edges, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PKA_B200_H */

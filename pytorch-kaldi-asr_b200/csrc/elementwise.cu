@@ -1,0 +1,347 @@
+// HBM-bound element-wise / gather / reduction pieces of the path, the fused Adam step, and library plumbing.
+// All kernels use 128-bit accesses where the shape allows, grid-stride loops sized in multiples of the SM count.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace pka {
+
+// ---------------------------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py reports it as gpu_launches)
+unsigned long long launch_count() { return g_launches; }
+int check_launch(const char* what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return PKA_ELAUNCH;
+  }
+  return PKA_OK;
+}
+
+static inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------- embedding + position
+template <typename T>
+__global__ void embed_pos_fwd_kernel(const long long* __restrict__ tok, const float* __restrict__ emb,
+                                     const float* __restrict__ pos, T* __restrict__ out, int B, int L, int D, int V,
+                                     const pka_dropout drop) {
+  DropCtx dc = make_drop(drop);
+  const int d4 = D >> 2;
+  const long long total = (long long)B * L * d4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d4) * 4;
+    const long long r = e / d4;
+    const int l = (int)(r % L);
+    long long t = tok[r];
+    if (t < 0 || t >= V) t = 0;
+    const float4 ev = *reinterpret_cast<const float4*>(emb + t * D + c);
+    const float4 pv = *reinterpret_cast<const float4*>(pos + (long long)l * D + c);
+    float4 o = make_float4(ev.x + pv.x, ev.y + pv.y, ev.z + pv.z, ev.w + pv.w);
+    if (dc.p > 0.f) {
+      const float4 m = dropout_mul4(dc, (unsigned long long)e);      // element index (r*D + c) >> 2 == e
+      o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+    }
+    st4(out + r * D + c, o);
+  }
+}
+
+// one CTA per vocabulary row: scan all tokens in order, accumulate matching rows -> deterministic scatter-add
+template <typename T>
+__global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __restrict__ dout,
+                                 float* __restrict__ demb, long long n_tok, int D, int padding_idx,
+                                 const pka_dropout drop) {
+  const int v = blockIdx.x;
+  if (v == padding_idx) return;
+  DropCtx dc = make_drop(drop);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = 0; r < n_tok; ++r) {
+      if (tok[r] == v) {
+        float g = to_f(dout[r * D + c]);
+        if (dc.p > 0.f) g = dropout_keep(dc, (unsigned long long)(r * D + c)) ? g * dc.scale : 0.f;
+        acc += g;
+      }
+    }
+    demb[(long long)v * D + c] += acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- + row vector, dropout
+template <typename T>
+__global__ void add_rowvec_dropout_kernel(const T* __restrict__ x, const float* __restrict__ rowvec,
+                                          T* __restrict__ out, long long rows, int D, int period,
+                                          const pka_dropout drop) {
+  DropCtx dc = make_drop(drop);
+  const int d4 = D >> 2;
+  const long long total = rows * d4;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d4) * 4;
+    const long long r = e / d4;
+    float4 o = ld4(x + r * D + c);
+    if (rowvec) {
+      const float4 pv = *reinterpret_cast<const float4*>(rowvec + (r % period) * D + c);
+      o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+    }
+    if (dc.p > 0.f) {
+      const float4 m = dropout_mul4(dc, (unsigned long long)e);
+      o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+    }
+    st4(out + r * D + c, o);
+  }
+}
+
+template <typename T>
+__global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long long n4, const pka_dropout drop) {
+  DropCtx dc = make_drop(drop);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    float4 g = ld4(dy + e * 4);
+    if (dc.p > 0.f) {
+      const float4 m = dropout_mul4(dc, (unsigned long long)e);
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    }
+    st4(dx + e * 4, g);
+  }
+}
+
+template <typename T>
+__global__ void relu_drop_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz,
+                                     long long n4, float scale) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 g = ld4(dy + e * 4), yv = ld4(y + e * 4);
+    float4 o;
+    o.x = yv.x > 0.f ? g.x * scale : 0.f;
+    o.y = yv.y > 0.f ? g.y * scale : 0.f;
+    o.z = yv.z > 0.f ? g.z * scale : 0.f;
+    o.w = yv.w > 0.f ? g.w * scale : 0.f;
+    st4(dz + e * 4, o);
+  }
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, const pka_dropout drop) {
+  DropCtx dc = make_drop(drop);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    keep[e] = (dc.p > 0.f) ? (dropout_keep(dc, (unsigned long long)e) ? 1 : 0) : 1;
+}
+
+// ---------------------------------------------------------------------------------------------- column sums
+constexpr int kColsumRowsPerChunk = 256;
+template <typename T>
+__global__ void colsum_part_kernel(const T* __restrict__ x, float* __restrict__ part, long long rows, int N, int ld) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long r0 = (long long)blockIdx.y * kColsumRowsPerChunk;
+  const long long r1 = r0 + kColsumRowsPerChunk < rows ? r0 + kColsumRowsPerChunk : rows;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += to_f(x[r * ld + n]);
+  part[(long long)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int chunks, int N, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(long long)c * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------- cast / transpose
+template <typename S, typename Dt>
+__global__ void cast_kernel(const S* __restrict__ s, Dt* __restrict__ d, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    d[e] = from_f<Dt>(to_f(s[e]));
+}
+template <typename S, typename Dt>
+__global__ void transpose_kernel(const S* __restrict__ s, Dt* __restrict__ d, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? to_f(s[(long long)r * cols + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) d[(long long)c * rows + r] = from_f<Dt>(tile[threadIdx.x][i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- optimiser
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const float* __restrict__ lr_dev, float lr_host,
+                            const long long* __restrict__ state, float b1, float b2, float eps,
+                            __nv_bfloat16* __restrict__ shadow) {
+  const long long t = state[0] + 1;
+  const float lr = lr_dev ? lr_dev[0] : lr_host;
+  // bias corrections in double (torch computes them on the host in double precision)
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float gv = g[e];
+    const float mv = b1 * m[e] + (1.f - b1) * gv;
+    const float vv = b2 * v[e] + (1.f - b2) * gv * gv;
+    m[e] = mv; v[e] = vv;
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    const float pv = p[e] - step_size * (mv / denom);
+    p[e] = pv;
+    if (shadow) shadow[e] = __float2bfloat16_rn(pv);
+  }
+}
+__global__ void adam_t_inc_kernel(long long* state) { state[0] += 1; }
+__global__ void lr_tick_kernel(float* lr, long long* state, float start_lr, float c) {
+  state[1] += 1;
+  lr[0] = (start_lr * c) / ((float)state[1] + c);
+}
+__global__ void counter_inc_kernel(unsigned long long* c) { c[0] += 1ull; }
+
+}  // namespace pka
+
+using namespace pka;
+
+extern "C" const char* pka_last_error(void) { return pka::g_err; }
+extern "C" int pka_version(void) { return 100; }
+extern "C" uint64_t pka_launch_count(void) { return pka::launch_count(); }
+extern "C" int pka_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  PKA_REQUIRE(e == cudaSuccess, PKA_EDEVICE, "check_device: %s", cudaGetErrorString(e));
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  PKA_REQUIRE(e == cudaSuccess, PKA_EDEVICE, "check_device: %s", cudaGetErrorString(e));
+  PKA_REQUIRE(major == 10, PKA_EDEVICE, "check_device: compute capability %d.x, this library is sm_100a only", major);
+  return PKA_OK;
+}
+
+#define DISPATCH_T(dtype, who, CALL)                                         \
+  if ((dtype) == PKA_F32) { using T = float; CALL; }                         \
+  else if ((dtype) == PKA_BF16) { using T = __nv_bfloat16; CALL; }           \
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, who ": dtype %d", (int)(dtype))
+
+extern "C" int pka_embed_pos_fwd(const int64_t* tok, const float* emb, const float* pos, void* out, int dtype, int B,
+                                 int L, int D, int V, const pka_dropout* drop, void* stream) {
+  PKA_REQUIRE(tok && emb && pos && out, PKA_EINVAL, "embed_pos_fwd: null pointer");
+  PKA_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, PKA_EUNSUPPORTED, "embed_pos_fwd: B=%d L=%d D=%d (D%%4)", B, L, D);
+  pka_dropout dr = drop ? *drop : no_dropout();
+  const long long total = (long long)B * L * (D / 4);
+  DISPATCH_T(dtype, "embed_pos_fwd", (embed_pos_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const long long*)tok, emb, pos, (T*)out, B, L, D, V, dr)));
+  return check_launch("embed_pos_fwd");
+}
+
+extern "C" int pka_embed_bwd(const int64_t* tok, const void* dout, float* demb, int dtype, int B, int L, int D, int V,
+                             int padding_idx, const pka_dropout* drop, void* stream) {
+  PKA_REQUIRE(tok && dout && demb, PKA_EINVAL, "embed_bwd: null pointer");
+  PKA_REQUIRE(B > 0 && L > 0 && D > 0 && V > 0, PKA_EINVAL, "embed_bwd: bad sizes");
+  pka_dropout dr = drop ? *drop : no_dropout();
+  const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
+  DISPATCH_T(dtype, "embed_bwd", (embed_bwd_kernel<T><<<V, threads, 0, as_stream(stream)>>>((const long long*)tok, (const T*)dout, demb, (long long)B * L, D, padding_idx, dr)));
+  return check_launch("embed_bwd");
+}
+
+extern "C" int pka_add_rowvec_dropout_fwd(const void* x, const float* rowvec, void* out, int dtype, int64_t rows, int D,
+                                          int period, const pka_dropout* drop, void* stream) {
+  PKA_REQUIRE(x && out, PKA_EINVAL, "add_rowvec_dropout_fwd: null pointer");
+  PKA_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && (!rowvec || period > 0), PKA_EUNSUPPORTED, "add_rowvec_dropout_fwd: rows=%lld D=%d", (long long)rows, D);
+  pka_dropout dr = drop ? *drop : no_dropout();
+  const long long total = rows * (D / 4);
+  DISPATCH_T(dtype, "add_rowvec_dropout_fwd", (add_rowvec_dropout_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, rowvec, (T*)out, rows, D, period, dr)));
+  return check_launch("add_rowvec_dropout_fwd");
+}
+
+extern "C" int pka_dropout_bwd(const void* dy, void* dx, int dtype, int64_t n, const pka_dropout* drop, void* stream) {
+  PKA_REQUIRE(dy && dx, PKA_EINVAL, "dropout_bwd: null pointer");
+  PKA_REQUIRE(n > 0 && n % 4 == 0, PKA_EUNSUPPORTED, "dropout_bwd: n=%lld must be a positive multiple of 4", (long long)n);
+  pka_dropout dr = drop ? *drop : no_dropout();
+  DISPATCH_T(dtype, "dropout_bwd", (dropout_bwd_kernel<T><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (T*)dx, n / 4, dr)));
+  return check_launch("dropout_bwd");
+}
+
+extern "C" int pka_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float scale, void* stream) {
+  PKA_REQUIRE(dy && y && dz, PKA_EINVAL, "relu_drop_bwd: null pointer");
+  PKA_REQUIRE(n > 0 && n % 4 == 0, PKA_EUNSUPPORTED, "relu_drop_bwd: n=%lld must be a positive multiple of 4", (long long)n);
+  DISPATCH_T(dtype, "relu_drop_bwd", (relu_drop_bwd_kernel<T><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dz, n / 4, scale)));
+  return check_launch("relu_drop_bwd");
+}
+
+extern "C" int pka_colsum_chunks(int64_t rows) { return (int)((rows + kColsumRowsPerChunk - 1) / kColsumRowsPerChunk); }
+
+extern "C" int pka_colsum(const void* x, float* out, float* part_ws, int dtype, int64_t rows, int N, int ld,
+                          int accumulate, void* stream) {
+  PKA_REQUIRE(x && out && part_ws, PKA_EINVAL, "colsum: null pointer");
+  PKA_REQUIRE(rows > 0 && N > 0 && ld >= N, PKA_EINVAL, "colsum: rows=%lld N=%d ld=%d", (long long)rows, N, ld);
+  const int chunks = pka_colsum_chunks(rows);
+  PKA_REQUIRE(chunks <= 65535, PKA_EUNSUPPORTED, "colsum: too many rows");
+  dim3 grid((N + 127) / 128, chunks);
+  DISPATCH_T(dtype, "colsum", (colsum_part_kernel<T><<<grid, 128, 0, as_stream(stream)>>>((const T*)x, part_ws, rows, N, ld)));
+  int rc = check_launch("colsum_part");
+  if (rc) return rc;
+  colsum_finish_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(part_ws, out, chunks, N, accumulate);
+  return check_launch("colsum_finish");
+}
+
+extern "C" int pka_dropout_mask(uint8_t* keep, int64_t n, const pka_dropout* drop, void* stream) {
+  PKA_REQUIRE(keep && drop && n > 0, PKA_EINVAL, "dropout_mask: bad arguments");
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(keep, n, *drop);
+  return check_launch("dropout_mask");
+}
+
+extern "C" int pka_cast(const void* src, int sd, void* dst, int dd, int64_t n, void* stream) {
+  PKA_REQUIRE(src && dst && n > 0, PKA_EINVAL, "cast: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(n, 256);
+  if (sd == PKA_F32 && dd == PKA_BF16) cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (sd == PKA_BF16 && dd == PKA_F32) cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (sd == PKA_F32 && dd == PKA_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (sd == PKA_BF16 && dd == PKA_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "cast: dtypes %d -> %d", sd, dd);
+  return check_launch("cast");
+}
+
+extern "C" int pka_transpose(const void* src, int sd, void* dst, int dd, int rows, int cols, void* stream) {
+  PKA_REQUIRE(src && dst && rows > 0 && cols > 0, PKA_EINVAL, "transpose: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  PKA_REQUIRE(grid.y <= 65535, PKA_EUNSUPPORTED, "transpose: too many rows");
+  if (sd == PKA_F32 && dd == PKA_BF16) transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, rows, cols);
+  else if (sd == PKA_BF16 && dd == PKA_F32) transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, rows, cols);
+  else if (sd == PKA_F32 && dd == PKA_F32) transpose_kernel<float, float><<<grid, block, 0, st>>>((const float*)src, (float*)dst, rows, cols);
+  else if (sd == PKA_BF16 && dd == PKA_BF16) transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "transpose: dtypes %d -> %d", sd, dd);
+  return check_launch("transpose");
+}
+
+extern "C" int pka_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* lr_dev, float lr_host, int64_t* state, float beta1, float beta2, float eps,
+                             void* bf16_shadow, void* stream) {
+  PKA_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, PKA_EINVAL, "adam_step: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
+  int rc = check_launch("adam");
+  if (rc) return rc;
+  adam_t_inc_kernel<<<1, 1, 0, st>>>((long long*)state);
+  return check_launch("adam_t_inc");
+}
+
+extern "C" int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream) {
+  PKA_REQUIRE(lr_dev && state, PKA_EINVAL, "lr_tick: null pointer");
+  lr_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(lr_dev, (long long*)state, start_lr, soft_coefficient);
+  return check_launch("lr_tick");
+}
+
+extern "C" int pka_counter_inc(uint64_t* counter, void* stream) {
+  PKA_REQUIRE(counter, PKA_EINVAL, "counter_inc: null pointer");
+  counter_inc_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long*)counter);
+  return check_launch("counter_inc");
+}

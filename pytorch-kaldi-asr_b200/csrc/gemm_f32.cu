@@ -1,0 +1,185 @@
+// fp32 SIMT GEMM family -- the "exact" path (bit-stable fp32 FMA accumulation in a fixed order), used for fp32
+// parity against the CPU oracle and for beam search, where token sequences must not flip.  The bf16 tensor-core
+// path lives in gemm_tc.cu.  Contract: include/pka_b200.h (pka_gemm_desc).
+//
+// One kernel template covers forward, data-gradient and weight-gradient of every linear map on the path
+// (BottleLinear, TDNN splice+Linear, per-head projections, Conv1d k=1) through four operand layouts, K "segments"
+// (splice contexts / heads) and a batch axis.  Frame splicing (reference ConcatLayer, L/pytorch/TDNN.py:20-28) is a
+// row shift with a bounds predicate inside the tile loader, so the [B,T,n_ctx*D] tensor is never materialised.
+#include "common.cuh"
+
+namespace pka {
+
+struct GemmParams {
+  const float* A; const float* B; float* C;
+  const float* bias; const float* residual;
+  int M, N, K, nseg;
+  int lda, ldb, ldc, ldr;
+  long long a_seg_off, b_seg_off, a_batch_off, b_batch_off, c_batch_off;
+  int shiftA[PKA_MAX_CTX];
+  int shiftB[PKA_MAX_CTX];
+  int T;
+  int relu, accumulate;
+  pka_dropout drop;
+};
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_f32_kernel(const GemmParams p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  static_assert(TM % 4 == 0 && TN % 4 == 0, "micro-tile is built from float4 groups");
+  static_assert(NT % 32 == 0 && BK == 32, "loader assumes one warp spans the contiguous tile dimension");
+  __shared__ __align__(16) float As[BK][LDA_S];
+  __shared__ __align__(16) float Bs[BK][LDB_S];
+
+  const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
+  constexpr int NW = NT / 32;
+  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN, batch = blockIdx.z;
+  const float* __restrict__ Ab = p.A + (long long)batch * p.a_batch_off;
+  const float* __restrict__ Bb = p.B + (long long)batch * p.b_batch_off;
+  float* __restrict__ Cb = p.C + (long long)batch * p.c_batch_off;
+  const int shiftB = p.shiftB[batch < PKA_MAX_CTX ? batch : 0];
+
+  // micro-tile: TM rows as TM/4 groups of 4 spaced BM/(TM/4) apart (conflict-free float4 smem reads), same for cols
+  constexpr int GM = TM / 4, GN = TN / 4;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int seg = 0; seg < p.nseg; ++seg) {
+    const float* __restrict__ As_g = Ab + (long long)seg * p.a_seg_off;
+    const float* __restrict__ Bs_g = Bb + (long long)seg * p.b_seg_off;
+    const int shA = p.shiftA[seg < PKA_MAX_CTX ? seg : 0];
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+      // ---- A tile -> As[k][m]
+      if (!TA) {                      // A[M,K] row-major: lanes along k
+        const int k = k0 + lane;
+        for (int r = wrow; r < BM; r += NW) {
+          const int m = m_blk + r;
+          float v = 0.f;
+          if (m < p.M && k < p.K) {
+            bool ok = true;
+            if (p.T > 0) { int t = m % p.T + shA; ok = (t >= 0) && (t < p.T); }
+            if (ok) v = As_g[(long long)(m + shA) * p.lda + k];
+          }
+          As[lane][r] = v;
+        }
+      } else {                        // A stored [K,M]: lanes along m
+        for (int kk = wrow; kk < BK; kk += NW) {
+          const int k = k0 + kk;
+#pragma unroll
+          for (int c = lane; c < BM; c += 32) {
+            const int m = m_blk + c;
+            As[kk][c] = (k < p.K && m < p.M) ? As_g[(long long)k * p.lda + m] : 0.f;
+          }
+        }
+      }
+      // ---- B tile -> Bs[k][n]
+      if (TB) {                       // B stored [N,K] (nn.Linear weight): lanes along k
+        const int k = k0 + lane;
+        for (int r = wrow; r < BN; r += NW) {
+          const int n = n_blk + r;
+          Bs[lane][r] = (n < p.N && k < p.K) ? Bs_g[(long long)n * p.ldb + k] : 0.f;
+        }
+      } else {                        // B stored [K,N]: lanes along n; optional frame shift on the reduction index
+        for (int kk = wrow; kk < BK; kk += NW) {
+          const int k = k0 + kk;
+          bool ok = k < p.K;
+          if (ok && p.T > 0) { int t = k % p.T + shiftB; ok = (t >= 0) && (t < p.T); }
+#pragma unroll
+          for (int c = lane; c < BN; c += 32) {
+            const int n = n_blk + c;
+            Bs[kk][c] = (ok && n < p.N) ? Bs_g[(long long)(k + shiftB) * p.ldb + n] : 0.f;
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < BK; ++kk) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int g = 0; g < GM; ++g) {
+          float4 v = *reinterpret_cast<const float4*>(&As[kk][g * (BM / GM) + ty * 4]);
+          a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int g = 0; g < GN; ++g) {
+          float4 v = *reinterpret_cast<const float4*>(&Bs[kk][g * (BN / GN) + tx * 4]);
+          b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias -> ReLU -> dropout -> + residual -> (accumulate) -> store
+  DropCtx dc = make_drop(p.drop);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m_blk + (i / 4) * (BM / GM) + ty * 4 + (i % 4);
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n_blk + (j / 4) * (BN / GN) + tx * 4 + (j % 4);
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (dc.p > 0.f) {
+        unsigned long long idx = ((unsigned long long)batch * p.M + m) * (unsigned long long)p.N + n;
+        v = dropout_keep(dc, idx) ? v * dc.scale : 0.f;
+      }
+      if (p.residual) v += p.residual[(long long)m * p.ldr + n];
+      float* dst = Cb + (long long)m * p.ldc + n;
+      if (p.accumulate) v += *dst;
+      *dst = v;
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+static int launch_cfg(const GemmParams& p, int transA, int transB, int nbatch, cudaStream_t st) {
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch);
+  dim3 block((BM / TM) * (BN / TN));
+  if (!transA && transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, true><<<grid, block, 0, st>>>(p);
+  else if (!transA && !transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, false><<<grid, block, 0, st>>>(p);
+  else if (transA && !transB) gemm_f32_kernel<BM, BN, 32, TM, TN, true, false><<<grid, block, 0, st>>>(p);
+  else gemm_f32_kernel<BM, BN, 32, TM, TN, true, true><<<grid, block, 0, st>>>(p);
+  return check_launch("gemm_f32");
+}
+
+}  // namespace pka
+
+extern "C" int pka_gemm_f32(const pka_gemm_desc* d, void* stream) {
+  using namespace pka;
+  PKA_REQUIRE(d && d->A && d->B && d->C, PKA_EINVAL, "gemm_f32: null operand");
+  PKA_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->nseg >= 1 && d->nbatch >= 1, PKA_EINVAL,
+              "gemm_f32: bad sizes M=%d N=%d K=%d nseg=%d nbatch=%d", d->M, d->N, d->K, d->nseg, d->nbatch);
+  PKA_REQUIRE(d->nseg <= PKA_MAX_CTX || d->T == 0, PKA_EUNSUPPORTED, "gemm_f32: more than %d spliced segments", PKA_MAX_CTX);
+  PKA_REQUIRE(d->nbatch <= PKA_MAX_CTX || d->T == 0 || d->transB, PKA_EUNSUPPORTED, "gemm_f32: more than %d shifted batches", PKA_MAX_CTX);
+  PKA_REQUIRE(d->T == 0 || (d->transA ? true : d->M % d->T == 0), PKA_EINVAL, "gemm_f32: M=%d is not a multiple of T=%d", d->M, d->T);
+  PKA_REQUIRE(d->T == 0 || !d->transA || d->transB || d->K % d->T == 0, PKA_EINVAL, "gemm_f32: K=%d is not a multiple of T=%d", d->K, d->T);
+  PKA_REQUIRE(d->nbatch <= 65535, PKA_EUNSUPPORTED, "gemm_f32: nbatch too large");
+  GemmParams p;
+  p.A = (const float*)d->A; p.B = (const float*)d->B; p.C = (float*)d->C;
+  p.bias = d->bias; p.residual = (const float*)d->residual;
+  p.M = d->M; p.N = d->N; p.K = d->K; p.nseg = d->nseg;
+  p.lda = d->lda; p.ldb = d->ldb; p.ldc = d->ldc; p.ldr = d->ldr;
+  p.a_seg_off = d->a_seg_off; p.b_seg_off = d->b_seg_off;
+  p.a_batch_off = d->a_batch_off; p.b_batch_off = d->b_batch_off; p.c_batch_off = d->c_batch_off;
+  for (int i = 0; i < PKA_MAX_CTX; ++i) { p.shiftA[i] = d->T > 0 ? d->shiftA[i] : 0; p.shiftB[i] = d->T > 0 ? d->shiftB[i] : 0; }
+  p.T = d->T; p.relu = d->relu; p.accumulate = d->accumulate; p.drop = d->drop;
+  cudaStream_t st = as_stream(stream);
+  // big tiles only when they still give >= ~1 wave of CTAs
+  long long big_ctas = (long long)((d->M + 127) / 128) * ((d->N + 127) / 128) * d->nbatch;
+  if (d->N >= 128 && big_ctas >= kNumSMs) return launch_cfg<128, 128, 8, 8>(p, d->transA, d->transB, d->nbatch, st);
+  return launch_cfg<64, 64, 4, 4>(p, d->transA, d->transB, d->nbatch, st);
+}

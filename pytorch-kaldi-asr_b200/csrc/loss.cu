@@ -1,0 +1,140 @@
+// Summed cross-entropy with PAD mask, optional label smoothing, fused arg-max accuracy (forward) and
+// (softmax - target) gradient (backward).  Replaces cal_loss / get_performance, L/train.py:58-90:
+//   plain:    loss = sum_{goal!=PAD} -log_softmax(x)[goal]                       (F.cross_entropy(ignore_index=0, 'sum'))
+//   smoothed: target = 1-eps on goal, eps/(V-1) on every other class (PAD/UNK/BOS columns included), eps = 0.1
+//   n_correct = #{goal!=PAD and argmax(x)==goal}  (first maximal index, like torch.max on CPU)
+// One warp per row; the final sum over rows is a fixed-order two-stage reduction (deterministic, no atomics).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace pka {
+
+constexpr int kCeWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kCeWarps * 32)
+ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal, int N, int V, int smoothing,
+              float eps, float* __restrict__ lse_o, float* __restrict__ part) {
+  __shared__ float red[kCeWarps][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float loss = 0.f, correct = 0.f, words = 0.f;
+  for (int row = blockIdx.x * kCeWarps + warp; row < N; row += gridDim.x * kCeWarps) {
+    const T* xr = logits + (long long)row * V;
+    float mx = -CUDART_INF_F;
+    int arg = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+      const float v = to_f(xr[c]);
+      if (v > mx) { mx = v; arg = c; }                 // strict > keeps the first index within a lane
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    float se = 0.f, sx = 0.f;
+    for (int c = lane; c < V; c += 32) {
+      const float v = to_f(xr[c]);
+      se += expf(v - mx);
+      sx += v;
+    }
+    se = warp_sum(se); sx = warp_sum(sx);
+    const float lse = mx + logf(se);
+    const long long g = goal[row];
+    if (lane == 0) {
+      lse_o[row] = lse;
+      if (g != 0) {
+        const float picked = to_f(xr[g]) - lse;          // log p[goal]
+        if (smoothing) {
+          const float off = eps / (float)(V - 1);
+          const float all = sx - (float)V * lse;         // sum_c log p[c]
+          loss += -((1.f - eps) * picked + off * (all - picked));
+        } else {
+          loss += -picked;
+        }
+        words += 1.f;
+        if ((long long)arg == g) correct += 1.f;
+      }
+    }
+  }
+  if (lane == 0) { red[warp][0] = loss; red[warp][1] = correct; red[warp][2] = words; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < kCeWarps; ++w) s += red[w][threadIdx.x];
+    part[blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void ce_finish_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out3) {
+  // three lanes, each sums one statistic over the CTAs in index order (fixed order => run-to-run identical)
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += part[b * 3 + threadIdx.x];
+    out3[threadIdx.x] = s;
+  }
+}
+
+template <typename T>
+__global__ void ce_bwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal,
+                              const float* __restrict__ lse, const float* __restrict__ grad_out, T* __restrict__ dl,
+                              int N, int V, int smoothing, float eps) {
+  const float go = grad_out ? grad_out[0] : 1.f;
+  const float off = smoothing ? eps / (float)(V - 1) : 0.f;
+  const float on = smoothing ? 1.f - eps : 1.f;
+  const long long total = (long long)N * V;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int row = e / V, c = e % V;
+    const long long g = goal[row];
+    float v = 0.f;
+    if (g != 0) {
+      const float pr = expf(to_f(logits[e]) - lse[row]);
+      // d/dx of -sum_c t_c log p_c = p*sum(t) - t ; sum(t) = 1 for both target distributions
+      v = go * (pr - (c == g ? on : off));
+    }
+    dl[e] = from_f<T>(v);
+  }
+}
+
+}  // namespace pka
+
+extern "C" int pka_ce_blocks(int N) {
+  int need = (N + pka::kCeWarps - 1) / pka::kCeWarps;
+  int cap = pka::kNumSMs * 2;
+  return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
+extern "C" int pka_ce_fwd(const void* logits, const int64_t* goal, int dtype, int N, int V, int smoothing, float eps,
+                          float* out3, float* lse, float* part_ws, void* stream) {
+  using namespace pka;
+  PKA_REQUIRE(logits && goal && out3 && lse && part_ws, PKA_EINVAL, "ce_fwd: null pointer");
+  PKA_REQUIRE(N > 0 && V > 1, PKA_EINVAL, "ce_fwd: N=%d V=%d", N, V);
+  const int nblk = pka_ce_blocks(N);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PKA_F32)
+    ce_fwd_kernel<float><<<nblk, kCeWarps * 32, 0, st>>>((const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+  else if (dtype == PKA_BF16)
+    ce_fwd_kernel<__nv_bfloat16><<<nblk, kCeWarps * 32, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_fwd: dtype %d", dtype);
+  int rc = check_launch("ce_fwd");
+  if (rc) return rc;
+  ce_finish_kernel<<<1, 32, 0, st>>>(part_ws, nblk, out3);
+  return check_launch("ce_finish");
+}
+
+extern "C" int pka_ce_bwd(const void* logits, const int64_t* goal, const float* lse, const float* grad_out,
+                          void* dlogits, int dtype, int N, int V, int smoothing, float eps, void* stream) {
+  using namespace pka;
+  PKA_REQUIRE(logits && goal && lse && dlogits, PKA_EINVAL, "ce_bwd: null pointer");
+  PKA_REQUIRE(N > 0 && V > 1, PKA_EINVAL, "ce_bwd: N=%d V=%d", N, V);
+  const long long total = (long long)N * V;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PKA_F32)
+    ce_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)logits, (const long long*)goal, lse, grad_out, (float*)dlogits, N, V, smoothing, eps);
+  else if (dtype == PKA_BF16)
+    ce_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)goal, lse, grad_out, (__nv_bfloat16*)dlogits, N, V, smoothing, eps);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_bwd: dtype %d", dtype);
+  return check_launch("ce_bwd");
+}

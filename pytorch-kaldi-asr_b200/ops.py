@@ -1,0 +1,488 @@
+"""torch.autograd.Function wrappers over the C ABI of libpka_b200.so.
+
+Every function here launches hand-written sm_100a kernels on torch's current stream; torch only provides memory,
+streams and the autograd tape.  Nothing falls back to ATen: non-CUDA tensors raise.
+
+Precision modes (module-level switch, see `set_compute_mode`):
+  "fp32": every GEMM runs the fp32 SIMT kernel with a fixed summation order (parity / exact beam search).
+  "bf16": GEMMs whose shapes fit the tcgen05 tiles run on the tensor cores with bf16 operands (fp32 master
+          weights, fp32 accumulation in TMEM); everything else stays fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_MODE = {"gemm": "fp32"}
+
+
+def set_compute_mode(mode: str):
+    assert mode in ("fp32", "bf16")
+    _MODE["gemm"] = mode
+
+
+def compute_mode() -> str:
+    return _MODE["gemm"]
+
+
+class Drop:
+    """One dropout call site of the reference: probability, site id, and the model's (seed, step counter)."""
+    __slots__ = ("p", "site", "seed", "step")
+
+    def __init__(self, p: float, site: int, seed: int, step: Optional[torch.Tensor]):
+        self.p, self.site, self.seed, self.step = float(p), int(site), int(seed), step
+
+    def c(self) -> L.Dropout:
+        return L.make_dropout(self.p, self.site, self.seed, self.step)
+
+    @property
+    def on(self) -> bool:
+        return self.p > 0.0
+
+
+def _cdrop(drop: Optional[Drop]) -> L.Dropout:
+    return drop.c() if (drop is not None and drop.on) else L.NO_DROPOUT
+
+
+def _byref_drop(drop: Optional[Drop]):
+    return C.byref(_cdrop(drop))
+
+
+# ------------------------------------------------------------------------------------------------ raw GEMM launcher
+def gemm(A, B, Cout, M, N, K, *, nseg=1, nbatch=1, lda, ldb, ldc, transA=False, transB=True, a_seg_off=0, b_seg_off=0,
+         a_batch_off=0, b_batch_off=0, c_batch_off=0, shiftA: Sequence[int] = (), shiftB: Sequence[int] = (), T=0,
+         bias=None, relu=False, drop: Optional[Drop] = None, residual=None, ldr=0, accumulate=False,
+         a_ptr_off=0, b_ptr_off=0, c_ptr_off=0):
+    """Launch pka_gemm_f32.  *_ptr_off are element offsets added to the base pointers (column blocks of packed buffers)."""
+    L.require_cuda(A, B, Cout)
+    if A.dtype != torch.float32 or B.dtype != torch.float32 or Cout.dtype != torch.float32:
+        raise RuntimeError("pka_gemm_f32 needs fp32 operands")
+    d = L.GemmDesc()
+    d.A = A.data_ptr() + 4 * a_ptr_off
+    d.B = B.data_ptr() + 4 * b_ptr_off
+    d.C = Cout.data_ptr() + 4 * c_ptr_off
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.residual = residual.data_ptr() if residual is not None else 0
+    d.M, d.N, d.K, d.nseg, d.nbatch = M, N, K, nseg, nbatch
+    d.lda, d.ldb, d.ldc, d.ldr = lda, ldb, ldc, ldr
+    d.transA, d.transB = int(transA), int(transB)
+    d.a_seg_off, d.b_seg_off = a_seg_off, b_seg_off
+    d.a_batch_off, d.b_batch_off, d.c_batch_off = a_batch_off, b_batch_off, c_batch_off
+    for i, s in enumerate(shiftA):
+        d.shiftA[i] = int(s)
+    for i, s in enumerate(shiftB):
+        d.shiftB[i] = int(s)
+    d.T = T
+    d.relu = int(relu)
+    d.accumulate = int(accumulate)
+    d.drop = _cdrop(drop)
+    L.check(L.lib().pka_gemm_f32(C.byref(d), L.stream_ptr()), "gemm_f32")
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, n = x2d.shape
+    acc = out is not None
+    if out is None:
+        out = torch.empty(n, device=x2d.device, dtype=torch.float32)
+    chunks = L.lib().pka_colsum_chunks(C.c_int64(rows))
+    ws = torch.empty(chunks * n, device=x2d.device, dtype=torch.float32)
+    L.check(L.lib().pka_colsum(L.ptr(x2d), L.ptr(out), L.ptr(ws), L.dtype_code(x2d), C.c_int64(rows), n, x2d.stride(0),
+                               int(acc), L.stream_ptr()), "colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ front-end
+def frontend(feats: torch.Tensor, lengths: Optional[torch.Tensor], fold: int, ctx: Sequence[int], cmvn_mode: int = 0,
+             out_dtype=torch.float32) -> torch.Tensor:
+    """[B,T,F] fp32 -> [B, T//fold, len(ctx)*F*fold]: optional CMVN, frame folding, frame splicing in one pass."""
+    L.require_cuda(feats, lengths)
+    feats = feats.contiguous()
+    B, T, F = feats.shape
+    out = torch.empty(B, T // fold, len(ctx) * F * fold, device=feats.device, dtype=out_dtype)
+    ctx_arr = (C.c_int32 * len(ctx))(*[int(c) for c in ctx])
+    stats = torch.empty(B * 2 * F, device=feats.device, dtype=torch.float32) if cmvn_mode else None
+    if lengths is not None:
+        lengths = lengths.to(torch.int32).contiguous()
+    L.check(L.lib().pka_frontend_fwd(L.ptr(feats), L.ptr(lengths), L.ptr(out), L.dtype_code(out), B, T, F, fold, ctx_arr,
+                                     len(ctx), cmvn_mode, L.ptr(stats), L.stream_ptr()), "frontend_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ linear family
+class _LinearFn(torch.autograd.Function):
+    """y = dropout(relu(splice_ctx(x) @ W^T + b)): BottleLinear / TDNNLayer / Conv1d(k=1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, splice, relu, drop, residual):
+        L.require_cuda(x, weight, bias, residual)
+        lead = x.shape[:-1]
+        kin = x.shape[-1]
+        x2 = x.reshape(-1, kin)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        n_ctx = len(splice) if splice else 1
+        w2 = weight.reshape(weight.shape[0], -1)
+        N = w2.shape[0]
+        assert w2.shape[1] == n_ctx * kin, "weight [%d,%d] does not match %d contexts x %d" % (N, w2.shape[1], n_ctx, kin)
+        T = x.shape[-2] if splice else 0
+        y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        r2 = None
+        if residual is not None:
+            assert not relu, "residual is added after dropout; combining it with ReLU is not a reference pattern"
+            r2 = residual.reshape(M, N).contiguous()
+        gemm(x2, w2, y, M, N, kin, nseg=n_ctx, lda=kin, ldb=n_ctx * kin, ldc=N, transB=True, b_seg_off=kin,
+             shiftA=splice or (), T=T, bias=bias, relu=relu, drop=drop, residual=r2, ldr=N)
+        ctx.save_for_backward(x2, w2, y if relu else None)
+        ctx.meta = (lead, kin, n_ctx, tuple(splice) if splice else (), T, relu, drop, bias is not None, weight.shape,
+                    residual is not None)
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w2, y = ctx.saved_tensors
+        lead, kin, n_ctx, splice, T, relu, drop, has_bias, wshape, has_res = ctx.meta
+        M, N = x2.shape[0], w2.shape[0]
+        dy2 = dy.reshape(M, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if relu:
+            dz = torch.empty_like(dy2)
+            scale = 1.0 / (1.0 - drop.p) if (drop is not None and drop.on) else 1.0
+            L.check(L.lib().pka_relu_drop_bwd(L.ptr(dy2), L.ptr(y), L.ptr(dz), L.PKA_F32, C.c_int64(M * N), C.c_float(scale),
+                                              L.stream_ptr()), "relu_drop_bwd")
+        elif drop is not None and drop.on:
+            dz = torch.empty_like(dy2)
+            L.check(L.lib().pka_dropout_bwd(L.ptr(dy2), L.ptr(dz), L.PKA_F32, C.c_int64(M * N), _byref_drop(drop),
+                                            L.stream_ptr()), "dropout_bwd")
+        else:
+            dz = dy2
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, kin, device=dy.device, dtype=torch.float32)
+            # dx[m,i] = sum_s sum_o dz[m - ctx_s, o] * W[o, s*kin + i]
+            gemm(dz, w2, dx, M, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * kin, ldc=kin, transB=False, b_seg_off=kin,
+                 shiftA=[-c for c in splice], T=T)
+            dx = dx.view(*lead, kin)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(N, n_ctx * kin, device=dy.device, dtype=torch.float32)
+            # dW[o, s*kin + i] = sum_m dz[m,o] * x[m + ctx_s, i]   (batch over contexts, frame shift on the reduction index)
+            gemm(dz, x2, dw, N, kin, M, nbatch=n_ctx, lda=N, ldb=kin, ldc=n_ctx * kin, transA=True, transB=False,
+                 c_batch_off=kin, shiftB=splice, T=T)
+            dw = dw.view(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dz)
+        dres = dy if (has_res and ctx.needs_input_grad[6]) else None
+        return dx, dw, db, None, None, None, dres
+
+
+def linear(x, weight, bias=None, splice: Optional[Sequence[int]] = None, relu: bool = False, drop: Optional[Drop] = None,
+           residual=None):
+    """dropout(relu(splice(x) @ W^T + b)) [+ residual]."""
+    return _LinearFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, residual)
+
+
+def affine_kn(x, weight_kn, bias=None):
+    """x @ W + b for a frozen [in, out] matrix (LDALayer, L/pytorch/TDNN.py:53-55).  No autograd: the reference keeps
+    these parameters requires_grad=False and the input is the feature tensor."""
+    L.require_cuda(x, weight_kn, bias)
+    lead, kin = x.shape[:-1], x.shape[-1]
+    x2 = x.detach().reshape(-1, kin)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    w = weight_kn.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    assert w.shape[0] == kin
+    N = w.shape[1]
+    y = torch.empty(x2.shape[0], N, device=x.device, dtype=torch.float32)
+    gemm(x2, w, y, x2.shape[0], N, kin, lda=kin, ldb=N, ldc=N, transB=False, bias=bias.detach() if bias is not None else None)
+    return y.view(*lead, N)
+
+
+class _HeadProjFn(torch.autograd.Function):
+    """Packed per-head projections: out[..., p*H*dk + h*dk + j] = sum_d x[..., d] * w_p[h, d, j] for p in 0..len(ws)-1.
+    Replaces q.repeat(n_head)+bmm (T/SubLayers.py:49-56): no replication, heads are column blocks."""
+
+    @staticmethod
+    def forward(ctx, x, *ws):
+        L.require_cuda(x, *ws)
+        lead, D = x.shape[:-1], x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        H, _, dk = ws[0].shape
+        P = len(ws)
+        out = torch.empty(M, P * H * dk, device=x.device, dtype=torch.float32)
+        for p, w in enumerate(ws):
+            assert w.shape == (H, D, dk) and w.is_contiguous()
+            gemm(x2, w, out, M, dk, D, nbatch=H, lda=D, ldb=dk, ldc=P * H * dk, transB=False, b_batch_off=D * dk,
+                 c_batch_off=dk, c_ptr_off=p * H * dk)
+        ctx.save_for_backward(x2, *ws)
+        ctx.meta = (lead, D, H, dk, P)
+        return out.view(*lead, P * H * dk)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, *ws = ctx.saved_tensors
+        lead, D, H, dk, P = ctx.meta
+        M = x2.shape[0]
+        dy2 = dy.reshape(M, P * H * dk)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, D, device=dy.device, dtype=torch.float32)
+            for p, w in enumerate(ws):
+                # dx[m,d] (+)= sum_h sum_j dy[m, p*H*dk + h*dk + j] * w_p[h,d,j]
+                gemm(dy2, w, dx, M, D, dk, nseg=H, lda=P * H * dk, ldb=dk, ldc=D, transB=True, a_seg_off=dk,
+                     b_seg_off=D * dk, a_ptr_off=p * H * dk, accumulate=(p > 0))
+            dx = dx.view(*lead, D)
+        dws = []
+        for p, w in enumerate(ws):
+            if not ctx.needs_input_grad[1 + p]:
+                dws.append(None)
+                continue
+            dw = torch.empty_like(w)
+            # dw_p[h,d,j] = sum_m x[m,d] * dy[m, p*H*dk + h*dk + j]
+            gemm(x2, dy2, dw, D, dk, M, nbatch=H, lda=D, ldb=P * H * dk, ldc=dk, transA=True, transB=False,
+                 b_batch_off=dk, c_batch_off=D * dk, b_ptr_off=p * H * dk)
+            dws.append(dw)
+        return (dx, *dws)
+
+
+def head_proj(x, *ws):
+    return _HeadProjFn.apply(x, *ws)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qbuf, kvbuf, key_mask, H, dk, band, scale, drop, want_probs):
+        """self-attention: qbuf = packed [B,L,3*H*dk] (q|k|v), kvbuf None.
+        cross-attention: qbuf = [B,Lq,H*dk], kvbuf = packed [B,Lk,2*H*dk] (k|v)."""
+        L.require_cuda(qbuf, kvbuf, key_mask)
+        qbuf = qbuf.contiguous()
+        HD = H * dk
+        B, Lq = qbuf.shape[0], qbuf.shape[1]
+        if kvbuf is None:
+            Lk, ldq = Lq, 3 * HD
+            q_p, k_p, v_p, ldk = qbuf.data_ptr(), qbuf.data_ptr() + 4 * HD, qbuf.data_ptr() + 8 * HD, 3 * HD
+        else:
+            kvbuf = kvbuf.contiguous()
+            Lk, ldq, ldk = kvbuf.shape[1], HD, 2 * HD
+            q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 4 * HD
+        key_mask = key_mask.to(torch.uint8).contiguous()
+        assert key_mask.shape == (B, Lk)
+        d = L.AttnDesc()
+        d.B, d.H, d.Lq, d.Lk, d.dk, d.dv = B, H, Lq, Lk, dk, dk
+        d.ldq, d.ldk, d.ldv, d.ldo = ldq, ldk, ldk, HD
+        d.use_band = int(band is not None)
+        d.band_start, d.band_end = (int(band[0]), int(band[1])) if band is not None else (0, 0)
+        d.scale = float(scale)
+        d.drop = _cdrop(drop)
+        out = torch.empty(B, Lq, HD, device=qbuf.device, dtype=torch.float32)
+        lse = torch.empty(B, H, Lq, device=qbuf.device, dtype=torch.float32)
+        probs = torch.empty(B, H, Lq, Lk, device=qbuf.device, dtype=torch.float32) if want_probs else None
+        L.check(L.lib().pka_attn_fwd(C.byref(d), L.PKA_F32, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
+                                     L.ptr(key_mask), L.ptr(out), L.ptr(lse), L.ptr(probs), L.stream_ptr()), "attn_fwd")
+        ctx.save_for_backward(qbuf, kvbuf, key_mask, out, lse)
+        ctx.desc = d
+        ctx.mark_non_differentiable(lse)
+        if probs is not None:
+            ctx.mark_non_differentiable(probs)
+        return out, lse, probs
+
+    @staticmethod
+    def backward(ctx, dout, _dlse, _dprobs):
+        qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
+        d = ctx.desc
+        HD = d.H * d.dk
+        dout = dout.contiguous()
+        dqbuf = torch.empty_like(qbuf)
+        if kvbuf is None:
+            dkvbuf = None
+            q_p, k_p, v_p = qbuf.data_ptr(), qbuf.data_ptr() + 4 * HD, qbuf.data_ptr() + 8 * HD
+            dq_p, dk_p, dv_p = dqbuf.data_ptr(), dqbuf.data_ptr() + 4 * HD, dqbuf.data_ptr() + 8 * HD
+        else:
+            dkvbuf = torch.empty_like(kvbuf)
+            q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 4 * HD
+            dq_p, dk_p, dv_p = dqbuf.data_ptr(), dkvbuf.data_ptr(), dkvbuf.data_ptr() + 4 * HD
+        delta = torch.empty_like(lse)
+        L.check(L.lib().pka_attn_bwd(C.byref(d), L.PKA_F32, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
+                                     L.ptr(key_mask), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta),
+                                     C.c_void_p(dq_p), C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_bwd")
+        return dqbuf, dkvbuf, None, None, None, None, None, None, None
+
+
+def attention(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, drop: Optional[Drop] = None,
+              want_probs: bool = False):
+    out, _lse, probs = _AttnFn.apply(qbuf, kvbuf, key_mask, n_head, d_k, band, scale, drop, want_probs)
+    return out, probs
+
+
+# ------------------------------------------------------------------------------------------------ add + LayerNorm
+class _AddLayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, a, b, eps, drop):
+        L.require_cuda(x, residual, a, b)
+        shape = x.shape
+        D = shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        r2 = residual.reshape(-1, D).contiguous() if residual is not None else None
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rinv = torch.empty(rows, device=x.device, dtype=torch.float32)
+        L.check(L.lib().pka_add_layernorm_fwd(L.ptr(x2), L.ptr(r2), L.ptr(a), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rinv),
+                                              L.dtype_code(x2), rows, D, C.c_float(eps), _byref_drop(drop), L.stream_ptr()),
+                "add_layernorm_fwd")
+        ctx.save_for_backward(x2, r2, a, mean, rinv)
+        ctx.meta = (shape, eps, drop)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, r2, a, mean, rinv = ctx.saved_tensors
+        shape, eps, drop = ctx.meta
+        rows, D = x2.shape
+        dy2 = dy.reshape(rows, D).contiguous()
+        dres = torch.empty_like(x2)
+        use_drop = drop is not None and drop.on
+        dx = torch.empty_like(x2) if use_drop else None
+        da = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        db = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        nblk = L.lib().pka_ln_bwd_blocks(rows)
+        ws = torch.empty(2 * D * nblk, device=dy.device, dtype=torch.float32)
+        L.check(L.lib().pka_add_layernorm_bwd(L.ptr(dy2), L.ptr(x2), L.ptr(r2), L.ptr(a), L.ptr(mean), L.ptr(rinv), L.ptr(dx),
+                                              L.ptr(dres), L.ptr(da), L.ptr(db), L.ptr(ws), L.dtype_code(x2), rows, D,
+                                              C.c_float(eps), _byref_drop(drop), L.stream_ptr()), "add_layernorm_bwd")
+        dres_v = dres.view(shape)
+        dx_v = dx.view(shape) if use_drop else dres_v
+        return dx_v, (dres_v if r2 is not None else None), da, db, None, None
+
+
+def add_layer_norm(x, residual, a, b, eps: float = 1e-3, drop: Optional[Drop] = None):
+    """LayerNormalization(dropout(x) + residual) with the reference's formula (T/Modules.py:42-51)."""
+    return _AddLayerNormFn.apply(x, residual, a, b, eps, drop)
+
+
+# ------------------------------------------------------------------------------------------------ embedding, positions
+class _EmbedPosFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, emb, pos, drop, padding_idx):
+        L.require_cuda(tok, emb, pos)
+        tok = tok.to(torch.int64).contiguous()
+        B, Ln = tok.shape
+        V, D = emb.shape
+        assert pos.shape[0] >= Ln, "sequence length %d exceeds the position table (%d)" % (Ln, pos.shape[0])
+        out = torch.empty(B, Ln, D, device=emb.device, dtype=torch.float32)
+        L.check(L.lib().pka_embed_pos_fwd(L.ptr(tok), L.ptr(emb), L.ptr(pos), L.ptr(out), L.PKA_F32, B, Ln, D, V,
+                                          _byref_drop(drop), L.stream_ptr()), "embed_pos_fwd")
+        ctx.save_for_backward(tok)
+        ctx.meta = (V, D, drop, padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tok,) = ctx.saved_tensors
+        V, D, drop, padding_idx = ctx.meta
+        B, Ln = tok.shape
+        dout = dout.contiguous()
+        demb = torch.zeros(V, D, device=dout.device, dtype=torch.float32)
+        L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.PKA_F32, B, Ln, D, V, padding_idx,
+                                      _byref_drop(drop), L.stream_ptr()), "embed_bwd")
+        return None, demb, None, None, None
+
+
+def embed_pos(tok, emb, pos, drop: Optional[Drop] = None, padding_idx: int = 0):
+    return _EmbedPosFn.apply(tok, emb, pos, drop, padding_idx)
+
+
+class _AddRowvecDropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rowvec, period, drop):
+        L.require_cuda(x, rowvec)
+        x = x.contiguous()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        if rowvec is not None:
+            assert rowvec.shape[0] >= period and rowvec.shape[1] == D and rowvec.is_contiguous()
+        out = torch.empty_like(x)
+        L.check(L.lib().pka_add_rowvec_dropout_fwd(L.ptr(x), L.ptr(rowvec), L.ptr(out), L.dtype_code(x), C.c_int64(rows), D,
+                                                   period, _byref_drop(drop), L.stream_ptr()), "add_rowvec_dropout_fwd")
+        ctx.drop = drop
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        drop = ctx.drop
+        if drop is None or not drop.on:
+            return dy, None, None, None
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(dx), L.dtype_code(dy), C.c_int64(dy.numel()), _byref_drop(drop),
+                                        L.stream_ptr()), "dropout_bwd")
+        return dx, None, None, None
+
+
+def add_pos_dropout(x, pos_table: Optional[torch.Tensor], drop: Optional[Drop] = None):
+    """dropout(x + pos_table[arange(x.size(1))]) (T/Models.py:164-165); pos_table None = plain dropout."""
+    if pos_table is None and (drop is None or not drop.on):
+        return x
+    period = x.shape[-2]
+    if pos_table is not None:
+        assert pos_table.shape[0] >= period, "sequence length %d exceeds the position table (%d)" % (period, pos_table.shape[0])
+    return _AddRowvecDropoutFn.apply(x, pos_table, period, drop)
+
+
+# ------------------------------------------------------------------------------------------------ loss
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits2d, goal, smoothing, eps):
+        L.require_cuda(logits2d, goal)
+        logits2d = logits2d.contiguous()
+        goal = goal.to(torch.int64).contiguous()
+        N, V = logits2d.shape
+        out3 = torch.empty(3, device=logits2d.device, dtype=torch.float32)
+        lse = torch.empty(N, device=logits2d.device, dtype=torch.float32)
+        nblk = L.lib().pka_ce_blocks(N)
+        ws = torch.empty(3 * nblk, device=logits2d.device, dtype=torch.float32)
+        L.check(L.lib().pka_ce_fwd(L.ptr(logits2d), L.ptr(goal), L.dtype_code(logits2d), N, V, int(smoothing),
+                                   C.c_float(eps), L.ptr(out3), L.ptr(lse), L.ptr(ws), L.stream_ptr()), "ce_fwd")
+        ctx.save_for_backward(logits2d, goal, lse)
+        ctx.meta = (int(smoothing), eps)
+        loss = out3[0]
+        stats = out3[1:]
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, gloss, _gstats):
+        logits2d, goal, lse = ctx.saved_tensors
+        smoothing, eps = ctx.meta
+        N, V = logits2d.shape
+        gl = gloss.contiguous().to(torch.float32)
+        dl = torch.empty_like(logits2d)
+        L.check(L.lib().pka_ce_bwd(L.ptr(logits2d), L.ptr(goal), L.ptr(lse), L.ptr(gl), L.ptr(dl), L.dtype_code(logits2d), N, V,
+                                   smoothing, C.c_float(eps), L.stream_ptr()), "ce_bwd")
+        return dl, None, None, None
+
+
+def cross_entropy_sum(logits2d, goal, smoothing: bool = False, eps: float = 0.1):
+    """-> (loss_sum scalar tensor, stats tensor [n_correct, n_words]); PAD (=0) targets ignored (L/train.py:58-90)."""
+    return _CrossEntropyFn.apply(logits2d, goal, bool(smoothing), float(eps))
+
+
+# ------------------------------------------------------------------------------------------------ test helper
+def dropout_keep_mask(n: int, drop: Drop, device) -> torch.Tensor:
+    """The keep bits (uint8[n]) the kernels derive for this site at the *current* step -- for parity tests only."""
+    keep = torch.empty(n, device=device, dtype=torch.uint8)
+    L.check(L.lib().pka_dropout_mask(L.ptr(keep), C.c_int64(n), C.byref(drop.c()), L.stream_ptr()), "dropout_mask")
+    return keep

@@ -1,0 +1,110 @@
+"""Data-parallel training over utterance batches: one process per GPU, NCCL all-reduce of the flat gradient arena.
+
+The reference is single-device; this is the new exchange step of 8(e).  Its loss is a SUM over tokens
+(L/train.py:86-88), so gradients are all-reduced with SUM and NOT divided by the world size: N ranks x B utterances then
+reproduce exactly the single-process gradient on the concatenated N*B batch.
+
+Overlap: parameters sit in the arena in forward order, so backward completes the arena from its tail.  The arena is cut
+into a few contiguous buckets; a post-accumulate hook counts finished tensors per bucket and, when a bucket is complete,
+launches its all-reduce on a side stream while backward continues on the compute stream.  `finish()` (called before the
+optimiser step) makes the compute stream wait for the communication stream.  Works with `gloo` on CPU tensors for tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) slice of `n_items` for `rank` (decode shards utterances with no collective)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def plan_buckets(offsets: List[int], sizes: List[int], total: int, n_buckets: int):
+    """Cut [0,total) into <= n_buckets contiguous ranges on tensor boundaries, roughly equal in bytes.
+    Returns (bounds [(lo,hi)...] in arena order, bucket index per tensor)."""
+    n_buckets = max(1, min(n_buckets, len(offsets)))
+    target = total / n_buckets
+    bounds, owner, lo, b = [], [], 0, 0
+    for i, (off, sz) in enumerate(zip(offsets, sizes)):
+        owner.append(b)
+        end = offsets[i + 1] if i + 1 < len(offsets) else total
+        if end - lo >= target and b < n_buckets - 1 and i + 1 < len(offsets):
+            bounds.append((lo, end))
+            lo, b = end, b + 1
+    bounds.append((lo, total))
+    return bounds, owner
+
+
+class GradAllReduce:
+    """Bucketed SUM all-reduce of `FusedAdam.flat_grad`, overlapped with backward.
+
+        sync = GradAllReduce(fused_adam, n_buckets=3)
+        loss.backward()            # hooks fire, buckets go out as they complete
+        sync.finish()              # before optimizer.step()
+    """
+
+    def __init__(self, optimizer, n_buckets: int = 3, group=None, overlap: bool = True):
+        self.opt = optimizer
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        params = optimizer._train
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        self.bounds, self.owner = plan_buckets(optimizer._offsets, sizes, optimizer.numel, n_buckets)
+        self.expected = [self.owner.count(b) for b in range(len(self.bounds))]
+        self.pending = list(self.expected)
+        self.overlap = overlap and self.world > 1
+        self.is_cuda = optimizer.flat_grad.is_cuda
+        self.comm_stream = torch.cuda.Stream() if (self.is_cuda and self.overlap) else None
+        self.launched = [False] * len(self.bounds)
+        self.handles = []
+        if self.overlap:
+            for i, p in enumerate(params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(_param):
+            b = self.owner[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        lo, hi = self.bounds[b]
+        view = self.opt.flat_grad[lo:hi]
+        self.launched[b] = True
+        if self.world == 1:
+            return
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Send whatever has not gone out yet (no-overlap mode: everything), then join communication and compute."""
+        for b in range(len(self.bounds)):
+            if not self.launched[b]:
+                self._launch(b)
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.pending = list(self.expected)
+        self.launched = [False] * len(self.bounds)
+
+    __call__ = finish
+
+
+def all_reduce_stats(totals: torch.Tensor, group=None) -> torch.Tensor:
+    """Per-epoch SUM of (loss, n_correct, n_words) across ranks (the three accumulators of L/train.py:203-214)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+    return totals

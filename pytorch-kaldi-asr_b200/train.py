@@ -1,0 +1,165 @@
+"""Training-loop side of the hot path with the reference's function names and signatures (L/train.py:58-214):
+`cal_loss`, `get_performance`, `train_epoch`.  The step itself -- forward, summed CE (+accuracy), backward, Adam, LR
+tick -- runs entirely as sm_100a kernels; `GraphedTrainStep` additionally captures it into one CUDA graph, which is
+what makes the tiny TIMIT model (launch-bound) run at GPU speed.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .utils import constants
+
+
+def cal_loss(pred, goal, smoothing):
+    """Summed cross-entropy over non-PAD targets; label smoothing eps=0.1 over the other V-1 classes when asked
+    (L/train.py:72-90).  `pred` [N,V] logits, `goal` [N]."""
+    loss, _ = ops.cross_entropy_sum(pred, goal.contiguous().view(-1), smoothing)
+    return loss
+
+
+def get_performance(crit, pred, goal, smoothing=True, num_class=None):
+    """-> (loss_sum, n_correct) like L/train.py:58-69; both come out of ONE kernel pass over the logits."""
+    pred2 = pred.contiguous().view(-1, pred.size(-1))
+    loss, stats = ops.cross_entropy_sum(pred2, goal.contiguous().view(-1), smoothing)
+    return loss, stats[0]
+
+
+def _to_device(batch, device, non_blocking=True):
+    """numpy batch tuple -> device tensors (the reference's FloatTensor/ByteTensor/LongTensor + .cuda(), L/train.py:151-161)."""
+    def put(x, dtype):
+        t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype) if not torch.is_tensor(x) else x.to(dtype)
+        return t.to(device, non_blocking=non_blocking)
+    return put(batch[1], torch.float32), put(batch[2], torch.uint8), put(batch[3], torch.int64), put(batch[4], torch.uint8)
+
+
+def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_eval=10, use_gpu=False, seq_error_prob=0,
+                smoothing=False, graphed: Optional["GraphedTrainStep"] = None):
+    """One pass over `batch_loader` (L/train.py:127-214).  Returns (loss per word, token accuracy).
+
+    Differences from the reference, all behaviour-preserving: the dead `use_seq_error` branches are not carried; the
+    label-smoothing switch the reference hard-wires to False (L/train.py:193) is a keyword (default False); the three
+    running totals stay on the device and are read back once per epoch.  This path has no CPU mode: the model must be
+    on a CUDA device (`use_gpu` is accepted for signature compatibility)."""
+    if mode == 'train':
+        model.train()
+        batch_loader.mode = 'drop'
+    elif mode == 'eval':
+        model.eval()
+        batch_loader.mode = 'all'
+        seen = 0
+    else:
+        raise ValueError('[ERROR] invalid epoch mode')
+    device = next(model.parameters()).device
+    if device.type != 'cuda':
+        raise RuntimeError("train_epoch: the B200 path has no CPU mode; move the model to a CUDA device first")
+    totals = torch.zeros(3, device=device, dtype=torch.float64)          # loss, n_correct, n_words
+
+    for batch in batch_loader:
+        src_seq, src_pad_mask, tgt_seq, tgt_pad_mask = _to_device(batch, device)
+        if graphed is not None and mode == 'train':
+            totals += graphed.step(src_seq, src_pad_mask, tgt_seq, tgt_pad_mask).double()
+            continue
+        goal = tgt_seq[:, 1:]
+        tgt_in = tgt_seq[:, :-1]
+        tgt_in_mask = tgt_pad_mask[:, :-1]
+        if mode == 'train':
+            optimizer.zero_grad()
+            pred = model(src_seq, src_pad_mask, tgt_in, tgt_in_mask)
+        else:
+            with torch.no_grad():
+                pred = model(src_seq, src_pad_mask, tgt_in, tgt_in_mask)
+        loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), smoothing)
+        if mode == 'train':
+            loss.backward()
+            optimizer.step()
+            optimizer.update_learning_rate()
+        totals[0] += loss.detach().double()
+        totals[1:] += stats.double()
+        if mode == 'eval':
+            seen += 1
+            if seen == batch_eval:
+                break
+    loss_sum, n_correct, n_words = totals.tolist()
+    return loss_sum / int(n_words), n_correct / int(n_words)
+
+
+class GraphedTrainStep:
+    """Whole training step (zero_grad, forward, loss, backward, [gradient all-reduce], Adam, LR tick, dropout tick)
+    captured once into a CUDA graph and replayed per batch.  Requires fixed batch shapes -- which is what the
+    reference's pre-loading BatchLoader produces (it pads the whole data set to one length, U/BatchLoader.py:33-36).
+
+    Inputs are copied into static device buffers; `step` returns a device tensor [loss_sum, n_correct, n_words]."""
+
+    def __init__(self, model, optimizer, example_batch, smoothing=False, grad_sync=None, warmup=3):
+        self.model, self.optimizer, self.smoothing, self.grad_sync = model, optimizer, smoothing, grad_sync
+        device = next(model.parameters()).device
+        src, smask, tgt, tmask = _to_device(example_batch, device, non_blocking=False)
+        self.src, self.smask, self.tgt, self.tmask = src.clone(), smask.clone(), tgt.clone(), tmask.clone()
+        self.out = torch.zeros(3, device=device, dtype=torch.float32)
+        model.train()
+        snap = self._snapshot()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # warm allocator pools & lazy state outside the capture
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self._restore(snap)                               # warm-up steps must not count as training
+
+    def _snapshot(self):
+        inner = getattr(self.optimizer, "optimizer", self.optimizer)
+        if not hasattr(inner, "flat_param"):
+            raise RuntimeError("GraphedTrainStep needs a FusedAdam (flat parameter arena) inside the optimizer")
+        rng = self.model.dropout_state
+        dev = self.src.device
+        return dict(tensors=[(t, t.clone()) for t in (inner.flat_param, inner.exp_avg, inner.exp_avg_sq, inner.dev_state,
+                                                      inner.dev_lr, rng.step_tensor(dev))],
+                    n=getattr(self.optimizer, "n_current_steps", None), lr=[g["lr"] for g in inner.param_groups])
+
+    def _restore(self, snap):
+        inner = getattr(self.optimizer, "optimizer", self.optimizer)
+        for t, saved in snap["tensors"]:
+            t.copy_(saved)
+        if inner.flat_shadow is not None:
+            inner.flat_shadow.copy_(inner.flat_param)
+        if snap["n"] is not None:
+            self.optimizer.n_current_steps = snap["n"]
+        for g, lr in zip(inner.param_groups, snap["lr"]):
+            g["lr"] = lr
+        torch.cuda.synchronize()
+
+    def _body(self):
+        goal = self.tgt[:, 1:]
+        self.optimizer.zero_grad()
+        pred = self.model(self.src, self.smask, self.tgt[:, :-1], self.tmask[:, :-1])
+        loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), self.smoothing)
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync()
+        self.optimizer.step()
+        self.optimizer.update_learning_rate()
+        self.out[0].copy_(loss.detach())
+        self.out[1:].copy_(stats)
+
+    def load(self, src, smask, tgt, tmask):
+        self.src.copy_(src, non_blocking=True)
+        self.smask.copy_(smask, non_blocking=True)
+        self.tgt.copy_(tgt, non_blocking=True)
+        self.tmask.copy_(tmask, non_blocking=True)
+
+    def step(self, src, smask, tgt, tmask):
+        if tuple(src.shape) != tuple(self.src.shape) or tuple(tgt.shape) != tuple(self.tgt.shape):
+            raise RuntimeError("GraphedTrainStep: batch shape %s/%s differs from the captured %s/%s; pad the data set "
+                               "to one length (synthetic.batches(pad_to='set'))" %
+                               (tuple(src.shape), tuple(tgt.shape), tuple(self.src.shape), tuple(self.tgt.shape)))
+        self.load(src, smask, tgt, tmask)
+        self.graph.replay()
+        return self.out

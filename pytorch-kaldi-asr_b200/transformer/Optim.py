@@ -1,0 +1,122 @@
+"""Optimiser side of the training step: the reference's `ScheduledOptim` wrapper (T/Optim.py:4-27) plus `FusedAdam`,
+which replaces torch.optim.Adam's per-tensor update over 72 tensors by ONE kernel over a flat parameter arena.
+
+Arena layout (HBM): all trainable parameters live back to back in one fp32 buffer (`flat_param`), their gradients in a
+second one (`flat_grad`, `p.grad` are views into it), Adam moments in two more.  One launch updates everything; under
+data parallelism the same flat gradient buffer is what NCCL all-reduces (parallel.py), in a few large buckets.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Adam(betas, eps, no weight decay, no amsgrad) with torch.optim.Adam's arithmetic (bias corrections in double,
+    denom = sqrt(v)/sqrt(bc2) + eps, step = lr/bc1), fused over the arena.  Parameters must already be on the GPU."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, bf16_shadow=False):
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._train = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+        if not self._train:
+            raise ValueError("FusedAdam: no trainable parameters")
+        dev = self._train[0].device
+        L.require_cuda(*self._train)
+        for p in self._train:
+            if p.dtype != torch.float32:
+                raise RuntimeError("FusedAdam: fp32 master parameters expected")
+        # 16-byte align every tensor inside the arena so kernels may use 128-bit accesses on the views
+        self._offsets, total = [], 0
+        for p in self._train:
+            self._offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.numel = total
+        self.flat_param = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_shadow = torch.zeros(total, device=dev, dtype=torch.bfloat16) if bf16_shadow else None
+        with torch.no_grad():
+            for p, off in zip(self._train, self._offsets):
+                view = self.flat_param[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+            if self.flat_shadow is not None:
+                self.flat_shadow.copy_(self.flat_param)
+        self.dev_state = torch.zeros(2, device=dev, dtype=torch.int64)        # {adam_t, n_current_steps}
+        self.dev_lr = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self.use_device_lr = False                                            # switched on by ScheduledOptim
+
+    def grad_view(self, p):
+        i = next(k for k, q in enumerate(self._train) if q is p)
+        off = self._offsets[i]
+        return self.flat_grad[off:off + p.numel()].view(p.shape)
+
+    def shadow_view(self, p):
+        i = next(k for k, q in enumerate(self._train) if q is p)
+        off = self._offsets[i]
+        return self.flat_shadow[off:off + p.numel()].view(p.shape)
+
+    def _adopt_grads(self):
+        """Make sure every p.grad *is* its arena view (a foreign .grad tensor is copied in; None counts as zero)."""
+        for p, off in zip(self._train, self._offsets):
+            view = self.flat_grad[off:off + p.numel()].view(p.shape)
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            else:
+                continue
+            p.grad = view
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._adopt_grads()
+        self.flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is None
+        self._adopt_grads()
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        lr_dev = L.ptr(self.dev_lr) if self.use_device_lr else C.c_void_p(0)
+        L.check(L.lib().pka_adam_step(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg),
+                                      L.ptr(self.exp_avg_sq), C.c_int64(self.numel), lr_dev, C.c_float(g["lr"]),
+                                      L.ptr(self.dev_state), C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]),
+                                      L.ptr(self.flat_shadow), L.stream_ptr()), "adam_step")
+
+
+class ScheduledOptim(object):
+    """lr_n = start_lr * c / (n + c), installed AFTER step n (so step 1 runs at the inner optimiser's constructor lr),
+    exactly as T/Optim.py:21-27.  With a FusedAdam inside, the schedule also advances on the device (one tiny kernel),
+    which keeps a captured CUDA graph of the whole step valid across replays."""
+
+    def __init__(self, optimizer, start_lr=0.001, soft_coefficient=500):
+        self.optimizer = optimizer
+        self.start_lr = start_lr
+        self.soft_coefficient = soft_coefficient
+        self.n_current_steps = 0
+        self._fused = isinstance(optimizer, FusedAdam)
+        if self._fused:
+            optimizer.use_device_lr = True
+
+    def step(self):
+        self.optimizer.step()
+
+    def zero_grad(self):
+        self.optimizer.zero_grad()
+
+    def update_learning_rate(self):
+        self.n_current_steps += 1
+        new_lr = (self.start_lr * self.soft_coefficient) / (self.n_current_steps + self.soft_coefficient)
+        for group in self.optimizer.param_groups:
+            group["lr"] = new_lr
+        if self._fused:
+            o = self.optimizer
+            L.check(L.lib().pka_lr_tick(L.ptr(o.dev_lr), L.ptr(o.dev_state), C.c_float(self.start_lr),
+                                        C.c_float(self.soft_coefficient), L.stream_ptr()), "lr_tick")
