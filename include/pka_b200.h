@@ -84,8 +84,9 @@ typedef struct {
   int32_t T;
   int32_t relu;
   int32_t accumulate;
-  int32_t reserved;
-  pka_dropout drop;
+  int32_t splitk;          /* >1: split the reduction over `splitk` CTAs per tile (nseg==1, no epilogue); partial */
+  pka_dropout drop;        /*     sums go to splitk_ws and are added in a fixed order (deterministic)             */
+  void* splitk_ws;         /* float[splitk*nbatch*M*N] */
 } pka_gemm_desc;
 int pka_gemm_f32(const pka_gemm_desc* d, void* stream);
 

@@ -29,8 +29,8 @@ class GemmDesc(C.Structure):
                 ("a_seg_off", C.c_int64), ("b_seg_off", C.c_int64),
                 ("a_batch_off", C.c_int64), ("b_batch_off", C.c_int64), ("c_batch_off", C.c_int64),
                 ("shiftA", C.c_int32 * MAX_CTX), ("shiftB", C.c_int32 * MAX_CTX),
-                ("T", C.c_int32), ("relu", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32),
-                ("drop", Dropout)]
+                ("T", C.c_int32), ("relu", C.c_int32), ("accumulate", C.c_int32), ("splitk", C.c_int32),
+                ("drop", Dropout), ("splitk_ws", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):

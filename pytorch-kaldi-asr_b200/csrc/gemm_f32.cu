@@ -7,6 +7,7 @@
 // (splice contexts / heads) and a batch axis.  Frame splicing (reference ConcatLayer, L/pytorch/TDNN.py:20-28) is a
 // row shift with a bounds predicate inside the tile loader, so the [B,T,n_ctx*D] tensor is never materialised.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pka {
 
@@ -20,6 +21,8 @@ struct GemmParams {
   int shiftB[PKA_MAX_CTX];
   int T;
   int relu, accumulate;
+  int splitk, nbatch;          // split-K: grid.z = nbatch*splitk, raw partial sums go to ws[split][batch][M][N]
+  float* ws;
   pka_dropout drop;
 };
 
@@ -35,7 +38,12 @@ gemm_f32_kernel(const GemmParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, wrow = tid >> 5;
   constexpr int NW = NT / 32;
-  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN, batch = blockIdx.z;
+  const int m_blk = blockIdx.y * BM, n_blk = blockIdx.x * BN;
+  const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+  // split-K (nseg == 1 only): this CTA reduces k in [k_begin, k_end)
+  const int k_chunk = ((p.K + p.splitk - 1) / p.splitk + BK - 1) / BK * BK;
+  const int k_begin = split * k_chunk;
+  const int k_end = min(p.K, k_begin + k_chunk);
   const float* __restrict__ Ab = p.A + (long long)batch * p.a_batch_off;
   const float* __restrict__ Bb = p.B + (long long)batch * p.b_batch_off;
   float* __restrict__ Cb = p.C + (long long)batch * p.c_batch_off;
@@ -54,14 +62,14 @@ gemm_f32_kernel(const GemmParams p) {
     const float* __restrict__ As_g = Ab + (long long)seg * p.a_seg_off;
     const float* __restrict__ Bs_g = Bb + (long long)seg * p.b_seg_off;
     const int shA = p.shiftA[seg < PKA_MAX_CTX ? seg : 0];
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
       // ---- A tile -> As[k][m]
       if (!TA) {                      // A[M,K] row-major: lanes along k
         const int k = k0 + lane;
         for (int r = wrow; r < BM; r += NW) {
           const int m = m_blk + r;
           float v = 0.f;
-          if (m < p.M && k < p.K) {
+          if (m < p.M && k < k_end) {
             bool ok = true;
             if (p.T > 0) { int t = m % p.T + shA; ok = (t >= 0) && (t < p.T); }
             if (ok) v = As_g[(long long)(m + shA) * p.lda + k];
@@ -74,7 +82,7 @@ gemm_f32_kernel(const GemmParams p) {
 #pragma unroll
           for (int c = lane; c < BM; c += 32) {
             const int m = m_blk + c;
-            As[kk][c] = (k < p.K && m < p.M) ? As_g[(long long)k * p.lda + m] : 0.f;
+            As[kk][c] = (k < k_end && m < p.M) ? As_g[(long long)k * p.lda + m] : 0.f;
           }
         }
       }
@@ -83,12 +91,12 @@ gemm_f32_kernel(const GemmParams p) {
         const int k = k0 + lane;
         for (int r = wrow; r < BN; r += NW) {
           const int n = n_blk + r;
-          Bs[lane][r] = (n < p.N && k < p.K) ? Bs_g[(long long)n * p.ldb + k] : 0.f;
+          Bs[lane][r] = (n < p.N && k < k_end) ? Bs_g[(long long)n * p.ldb + k] : 0.f;
         }
       } else {                        // B stored [K,N]: lanes along n; optional frame shift on the reduction index
         for (int kk = wrow; kk < BK; kk += NW) {
           const int k = k0 + kk;
-          bool ok = k < p.K;
+          bool ok = k < k_end;
           if (ok && p.T > 0) { int t = k % p.T + shiftB; ok = (t >= 0) && (t < p.T); }
 #pragma unroll
           for (int c = lane; c < BN; c += 32) {
@@ -120,6 +128,20 @@ gemm_f32_kernel(const GemmParams p) {
     }
   }
 
+  if (p.splitk > 1) {              // raw partial sums; splitk_reduce_kernel finishes in a fixed order
+    float* wsb = p.ws + ((long long)split * p.nbatch + batch) * p.M * p.N;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m_blk + (i / 4) * (BM / GM) + ty * 4 + (i % 4);
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = n_blk + (j / 4) * (BN / GN) + tx * 4 + (j % 4);
+        if (n < p.N) wsb[(long long)m * p.N + n] = acc[i][j];
+      }
+    }
+    return;
+  }
   // ---- epilogue: bias -> ReLU -> dropout -> + residual -> (accumulate) -> store
   DropCtx dc = make_drop(p.drop);
 #pragma unroll
@@ -145,9 +167,22 @@ gemm_f32_kernel(const GemmParams p) {
   }
 }
 
+__global__ void splitk_reduce_kernel(const GemmParams p) {
+  const long long per = (long long)p.M * p.N, total = per * p.nbatch;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int batch = (int)(e / per);
+    const long long r = e % per;
+    const int m = (int)(r / p.N), n = (int)(r % p.N);
+    float s = 0.f;
+    for (int sp = 0; sp < p.splitk; ++sp) s += p.ws[(long long)sp * total + e];
+    float* dst = p.C + (long long)batch * p.c_batch_off + (long long)m * p.ldc + n;
+    *dst = p.accumulate ? *dst + s : s;
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 static int launch_cfg(const GemmParams& p, int transA, int transB, int nbatch, cudaStream_t st) {
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch * p.splitk);
   dim3 block((BM / TM) * (BN / TN));
   if (!transA && transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, true><<<grid, block, 0, st>>>(p);
   else if (!transA && !transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, false><<<grid, block, 0, st>>>(p);
@@ -177,9 +212,22 @@ extern "C" int pka_gemm_f32(const pka_gemm_desc* d, void* stream) {
   p.a_batch_off = d->a_batch_off; p.b_batch_off = d->b_batch_off; p.c_batch_off = d->c_batch_off;
   for (int i = 0; i < PKA_MAX_CTX; ++i) { p.shiftA[i] = d->T > 0 ? d->shiftA[i] : 0; p.shiftB[i] = d->T > 0 ? d->shiftB[i] : 0; }
   p.T = d->T; p.relu = d->relu; p.accumulate = d->accumulate; p.drop = d->drop;
+  p.splitk = d->splitk > 1 ? d->splitk : 1; p.nbatch = d->nbatch; p.ws = (float*)d->splitk_ws;
+  if (p.splitk > 1) {
+    PKA_REQUIRE(d->nseg == 1 && !d->bias && !d->relu && !d->residual && d->drop.p == 0.f, PKA_EUNSUPPORTED, "gemm_f32: split-K needs nseg=1 and no epilogue");
+    PKA_REQUIRE(p.ws, PKA_EINVAL, "gemm_f32: split-K workspace missing");
+    PKA_REQUIRE((long long)d->nbatch * p.splitk <= 65535, PKA_EUNSUPPORTED, "gemm_f32: nbatch*splitk too large");
+  }
   cudaStream_t st = as_stream(stream);
   // big tiles only when they still give >= ~1 wave of CTAs
-  long long big_ctas = (long long)((d->M + 127) / 128) * ((d->N + 127) / 128) * d->nbatch;
-  if (d->N >= 128 && big_ctas >= kNumSMs) return launch_cfg<128, 128, 8, 8>(p, d->transA, d->transB, d->nbatch, st);
-  return launch_cfg<64, 64, 4, 4>(p, d->transA, d->transB, d->nbatch, st);
+  long long big_ctas = (long long)((d->M + 127) / 128) * ((d->N + 127) / 128) * d->nbatch * p.splitk;
+  bool big = d->N >= 128 && big_ctas >= kNumSMs;
+  if (const char* force = getenv("PKA_GEMM_TILE")) big = (force[0] == 'b');     // diagnostics only
+  int rc = big ? launch_cfg<128, 128, 8, 8>(p, d->transA, d->transB, d->nbatch, st)
+               : launch_cfg<64, 64, 4, 4>(p, d->transA, d->transB, d->nbatch, st);
+  if (rc || p.splitk == 1) return rc;
+  long long total = (long long)p.M * p.N * p.nbatch;
+  int blocks = (int)((total + 255) / 256 < (long long)kNumSMs * 8 ? (total + 255) / 256 : (long long)kNumSMs * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+  return check_launch("gemm_f32 split-K reduce");
 }

@@ -67,13 +67,19 @@ def test_linear_fwd_bwd(B, T, kin, N, ctx, relu):
     w = rnd(N, n_ctx * kin, seed=2, scale=1.0 / math.sqrt(n_ctx * kin))
     b = rnd(N, seed=3, scale=0.1)
     gy = rnd(B, T, N, seed=4)
-    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
-    ref = F.linear(am.splice(xr, ctx) if ctx else xr, wr, br)
-    ref = torch.relu(ref) if relu else ref
-    ref.backward(gy)
     xg, wg, bg = [t.clone().to(DEV).requires_grad_(True) for t in (x, w, b)]
     out = o.linear(xg, wg, bg, splice=ctx, relu=relu)
     out.backward(gy.to(DEV))
+    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    ref = F.linear(am.splice(xr, ctx) if ctx else xr, wr, br)
+    if relu:
+        # the ReLU gate of a pre-activation that is zero to rounding (|z| ~ 1e-7) may legitimately differ between two
+        # fp32 summation orders; take the gate from the kernel output, after checking it only differs at such points
+        gate = out.detach().cpu() > 0
+        flips = gate != (ref.detach() > 0)
+        assert float(ref.detach()[flips].abs().max()) < 1e-5 if flips.any() else True
+        ref = ref * gate
+    ref.backward(gy)
     assert_close(out, ref, 1e-4, "linear fwd")
     assert_close(xg.grad, xr.grad, 1e-3, "linear dx")
     assert_close(wg.grad, wr.grad, 1e-3, "linear dW")
