@@ -181,27 +181,34 @@ int pka_counter_inc(uint64_t* counter, void* stream);
 
 /* ---- (e) beam-search decoding ------------------------------------------------------------------------------------
  * replaces: the per-step body of translate_batch (L/decode.py:54-98) + Lattice.advance (T/Lattice.py:35-81).
- * See pytorch-kaldi-asr_b200/decode.py for the device-resident lattice layout these operate on. */
+ * Device-resident lattice, one row per utterance, E = max_edges >= 1 + beam*max_len (edge 0 = BOS):
+ *   edge_prev/edge_word/edge_depth int32[n_utt,E], edge_weight f64[n_utt,E], n_edges int32[n_utt]
+ *   beam_edges int32[n_utt,beam] + beam_count int32[n_utt]: current beam, best first (finished edges stay in it)
+ *   slot_edge/slot_active int32[n_utt,beam]: live hypotheses in beam order = rows (u*beam+slot) of the decoder step
+ *   curr_length/done int32[n_utt], n_not_done int32[1] */
 typedef struct {
   int32_t n_utt, beam, V, max_edges, max_len;
   int32_t eos, force_full_length;
+  int32_t inputs_are_logprobs;   /* 1: `logits` already holds log-probabilities (Lattice.advance API); skip the log-softmax */
 } pka_beam_desc;
-/* log-softmax over V of logits[n_utt*beam, V] (fp32), candidate scores in fp64 = parent weight + log-prob, finished
- * hypotheses appended, warp-level top-`beam` with lowest-flat-index tie rule, lattice arrays updated in place. */
+/* fp32 log-softmax of logits[n_utt*beam, V] rows of live slots; candidate = parent weight (f64) + log-prob; finished
+ * hypotheses appended; warp-shuffle top-`beam` (ties -> lowest flat index); lattice and slots rewritten in place.
+ * force_full_length: the EOS log-prob is set to -1e30 (benchmark stress variant: nobody ever finishes). */
 int pka_beam_advance(const pka_beam_desc* d, const float* logits, int32_t* edge_prev, int32_t* edge_word,
-                     double* edge_weight, int32_t* n_edges, int32_t* beam_edges, int32_t* beam_count,
-                     int32_t* slot_edge, int32_t* slot_active, int32_t* curr_length, int32_t* done,
-                     int32_t* n_not_done, void* stream);
-/* tree attention over the lattice: the query of slot s (edge e) attends to e and its <= (-band_start) ancestors.
- * kcache/vcache f32[n_utt, max_edges, H*dk] hold the keys/values written when each edge was the newest token. */
-int pka_tree_attn(const float* q, const float* kcache, const float* vcache, const int32_t* edge_prev,
-                  const int32_t* slot_edge, const int32_t* slot_active, float* out, int n_utt, int beam, int max_edges,
-                  int H, int dk, int ldq, int window, float scale, void* stream);
-/* scatter the new token's K/V rows (slot-major [n_utt*beam, ld]) into the per-edge caches */
+                     int32_t* edge_depth, double* edge_weight, int32_t* n_edges, int32_t* beam_edges,
+                     int32_t* beam_count, int32_t* slot_edge, int32_t* slot_active, int32_t* curr_length,
+                     int32_t* done, int32_t* n_not_done, void* stream);
+/* self-attention of the newest token of every live slot over itself (k_self/v_self rows of the packed qkv buffer,
+ * leading dimension ld) and its <= window-1 ancestors, read from the per-edge caches kcache/vcache
+ * f32[n_utt, E, H*dk] along edge_prev.  out f32[n_utt*beam, H*dk]; dead slots give zeros. */
+int pka_tree_attn(const float* q, const float* k_self, const float* v_self, int ld, const float* kcache,
+                  const float* vcache, const int32_t* edge_prev, const int32_t* slot_edge, const int32_t* slot_active,
+                  float* out, int n_utt, int beam, int max_edges, int H, int dk, int window, float scale, void* stream);
+/* scatter the newest token's K/V rows (slot-major, leading dimension ld) into the per-edge caches */
 int pka_kv_append(const float* k_new, const float* v_new, int ld, float* kcache, float* vcache,
                   const int32_t* slot_edge, const int32_t* slot_active, int n_utt, int beam, int max_edges, int HD,
                   void* stream);
-/* decoder input of every slot: emb[word(edge)] + pos[depth(edge)] */
+/* decoder input of every slot: emb[word(edge)] + pos[depth(edge)]; dead slots give zeros */
 int pka_beam_embed(const float* emb, const float* pos, const int32_t* edge_word, const int32_t* edge_depth,
                    const int32_t* slot_edge, const int32_t* slot_active, float* out, int n_utt, int beam,
                    int max_edges, int D, void* stream);

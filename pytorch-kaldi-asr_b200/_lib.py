@@ -42,7 +42,8 @@ class AttnDesc(C.Structure):
 
 class BeamDesc(C.Structure):
     _fields_ = [("n_utt", C.c_int32), ("beam", C.c_int32), ("V", C.c_int32), ("max_edges", C.c_int32),
-                ("max_len", C.c_int32), ("eos", C.c_int32), ("force_full_length", C.c_int32)]
+                ("max_len", C.c_int32), ("eos", C.c_int32), ("force_full_length", C.c_int32),
+                ("inputs_are_logprobs", C.c_int32)]
 
 
 _lib = None

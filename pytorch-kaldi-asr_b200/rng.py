@@ -36,6 +36,9 @@ class DropoutState:
 
     def tick(self, device):
         """Advance the step counter on the device (stream ordered, graph capturable)."""
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("libpka_b200 ops run on CUDA (sm_100a) tensors only; got device %s. "
+                               "There is no CPU fallback." % (device,))
         t = self.step_tensor(device)
         L.check(L.lib().pka_counter_inc(L.ptr(t), L.stream_ptr()), "counter_inc")
 
