@@ -90,12 +90,38 @@ typedef struct {
 } pka_gemm_desc;
 int pka_gemm_f32(const pka_gemm_desc* d, void* stream);
 
-/* ---- (c) GEMM family, bf16 tcgen05/TMEM/TMA path ---------------------------------------------------------------
- * Same contract, restricted to what the tensor-core tiles support: A bf16 [rows, K] row-major (optionally a
- * [B,T,K] view with per-segment frame shifts done by 3-D TMA out-of-bounds zero fill), B bf16 [N, nseg*K] row-major
- * ("weight" layout, transB=1), fp32 accumulation in TMEM, epilogue bias/ReLU/dropout/residual, C bf16 or fp32.
- * tmap_ws: 3*128 bytes of *host* scratch for the CUtensorMap objects (passed as __grid_constant__). */
-int pka_gemm_bf16_tc(const pka_gemm_desc* d, int c_dtype, void* stream);
+/* ---- (c) GEMM family, bf16 tcgen05 / TMEM / TMA path ------------------------------------------------------------
+ * UMMA 128x128x16 tiles (tcgen05.mma, fp32 accumulation in TMEM), operands staged by TMA with 128B swizzle through a
+ * 4-stage mbarrier ring.  Activations are described to TMA as 3-D tensors [utterance, frame, feature], so the frame
+ * splice of a TDNN layer is `nseg` shifted boxes accumulating into one TMEM tile and TMA's out-of-bounds zero fill IS
+ * ConcatLayer's zero padding (L/pytorch/TDNN.py:20-28).
+ *   mode 0: C[b,t,:] = epi( sum_seg A[b, t+shift[seg], seg*a_seg_col : +K] . B[:, seg*b_seg_col : +K]^T )
+ *           A bf16 [Bt,T,lda], B bf16 [N,ldb] (nn.Linear layout or pka_weight_relayout's data-gradient layout),
+ *           C bf16/fp32 [Bt*T, ldc]; epilogue + bias[n], ReLU, dropout; Ct (optional) = bf16 transposed copy
+ *           [N, Bt, Tp] (Tp = T rounded up to 8) that mode 1 consumes.
+ *   mode 1: weight gradient  dW[o, seg*N + i] = sum_{b,t} A[o,b,t] * B[i,b,t+shift[seg]]   with A = dZt [M,Bt,Tp],
+ *           B = Xt [N,Bt,Tp] (both transposed activations, bf16); the frame reduction is split over `splits` CTAs
+ *           per tile, C = fp32 partials [splits, M, ldc] (ldc = nseg*N), summed by pka_tc_reduce in fixed order.
+ * replaces: TDNNLayer / BottleLinear / LDALayer GEMMs and their backward in the bf16 training path. */
+typedef struct {
+  const void* A; const void* B; void* C; void* Ct;
+  const float* bias;
+  int32_t mode, Bt, T, Tp;
+  int32_t M, N, K, nseg;
+  int32_t lda, ldb, ldc;
+  int32_t a_seg_col, b_seg_col;
+  int32_t shift[PKA_MAX_CTX];
+  int32_t relu, c_dtype, splits, reserved;
+  pka_dropout drop;
+} pka_tc_desc;
+int pka_gemm_tc(const pka_tc_desc* d, void* stream);
+/* out[e] (+)= sum_{s<splits} ws[s*per + e] */
+int pka_tc_reduce(const float* ws, float* out, int64_t per, int splits, int accumulate, void* stream);
+/* fp32 W[N, nseg*K] -> Wf bf16 (same layout, forward operand) and/or Wd bf16 [K, nseg*N], Wd[i, s*N+o] = W[o, s*K+i] */
+int pka_weight_relayout(const float* W, void* Wf, void* Wd, int N, int K, int nseg, void* stream);
+/* dZ = gate ? ((Y > 0) ? dY*scale : 0) : dY, bf16, written row-major [Bt*T, N] (dZ) and transposed [N, Bt, Tp] (dZt) */
+int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, void* dZ, void* dZt, int Bt, int T, int Tp, int N,
+                      float scale, int gate, void* stream);
 
 /* ---- (b) attention ----------------------------------------------------------------------------------------------
  * replaces: ScaledDotProductAttention.forward (T/Modules.py:75-97) with the masks of T/Models.py:27-49 evaluated

@@ -41,6 +41,8 @@ class TDNNLayer(nn.Module):
 
     def forward(self, x):
         drop = self._rng.make(self.p, self._site, x.device, self.training)
+        if x.dtype == torch.bfloat16:          # bf16 path: n_ctx shifted TMA boxes accumulate into one TMEM tile
+            return ops.linear_tc(x, self.proj.weight, self.proj.bias, splice=self.concat.index, relu=True, drop=drop)
         return ops.linear(x, self.proj.weight, self.proj.bias, splice=self.concat.index, relu=True, drop=drop)
 
 
@@ -55,4 +57,6 @@ class LDALayer(nn.Module):
         self.bias = nn.Parameter(mat[:, -1].contiguous(), requires_grad=False)
 
     def forward(self, x):
+        if x.dtype == torch.bfloat16:
+            return ops.affine_tc(x, self.weight, self.bias)
         return ops.affine_kn(x, self.weight, self.bias)

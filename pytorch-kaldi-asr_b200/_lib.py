@@ -33,6 +33,17 @@ class GemmDesc(C.Structure):
                 ("drop", Dropout), ("splitk_ws", C.c_void_p)]
 
 
+class TcDesc(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("Ct", C.c_void_p), ("bias", C.c_void_p),
+                ("mode", C.c_int32), ("Bt", C.c_int32), ("T", C.c_int32), ("Tp", C.c_int32),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nseg", C.c_int32),
+                ("lda", C.c_int32), ("ldb", C.c_int32), ("ldc", C.c_int32),
+                ("a_seg_col", C.c_int32), ("b_seg_col", C.c_int32),
+                ("shift", C.c_int32 * MAX_CTX),
+                ("relu", C.c_int32), ("c_dtype", C.c_int32), ("splits", C.c_int32), ("reserved", C.c_int32),
+                ("drop", Dropout)]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("dk", C.c_int32),
                 ("dv", C.c_int32), ("ldq", C.c_int32), ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32),

@@ -1,0 +1,464 @@
+// bf16 tensor-core GEMM family for sm_100a: tcgen05.mma (UMMA 128x128x16, cta_group::1) with fp32 accumulators in
+// TMEM, operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring, warp-specialised:
+//   warp 0    TMA producer (one elected lane)
+//   warp 1    MMA issuer   (one elected lane; tcgen05.commit releases smem stages / publishes the accumulator)
+//   warp 2    TMEM allocator
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / dropout -> global stores
+//
+// Frame splicing (reference ConcatLayer, L/pytorch/TDNN.py:20-28) costs nothing here: the activation tensor is
+// described to TMA as a 3-D tensor [utterance, frame, feature]; context c of a TDNN layer is the same box shifted by
+// ctx[c] frames, and TMA's out-of-bounds ZERO FILL reproduces ConcatLayer's zero padding at the tensor edges.  The
+// n_ctx shifted boxes are n_ctx K-segments accumulating into one TMEM tile, so [B,T,n_ctx*D] never exists.
+//
+// mode 0 ("rows"):   C[b,t,:] = epi( sum_seg A[b, t+shift[seg], :] . W[:, seg]^T )       forward and data-gradient
+//                    one CTA per (utterance, 128-frame tile, 128-column tile); optional transposed copy Ct[n, b, t]
+//                    (coalesced for free: a TMEM lane is an output row) which is what mode 1 consumes.
+// mode 1 ("wgrad"):  dW[o, seg*Ki+i] = sum_{b,t} dZt[o,b,t] * Xt[i,b,t+shift[seg]]       weight-gradient
+//                    both operands are the transposed activations (frames contiguous = K-major), reduction over all
+//                    frames is split over `splits` CTAs per tile (fp32 partials, summed in fixed order afterwards).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace pka {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int mode, Bt, T, N, K, nseg;
+  int kb_per_seg, tiles_per_utt;
+  int a_seg_col, b_seg_col;
+  int shift[PKA_MAX_CTX];
+  void* C; void* Ct;
+  int ldc, c_dtype, Tp;
+  const float* bias;
+  int relu;
+  int M;                       // mode 1: rows of dZt (output channels)
+  int utt_per_split, tb_per_utt;
+  pka_dropout drop;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major tile of [rows][64 bf16] written by TMA with 128B swizzle (8-row atoms of 1 KB)
+// (lbo_bytes = 16, unused) -- or an MN-major tile made of [64 k-rows][64 bf16] TMA boxes: 8 k-rows x 128 B atoms,
+// SBO = 1024 B between 8-row k groups, LBO = byte distance between consecutive 64-element MN blocks.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address            bits [0,14)
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;         // leading byte offset
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);       // A and B MN-major (mode 2)
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int b0 = 0, t0 = 0, n0 = 0, seg_fixed = 0, num_k_iters, b_lo = 0;
+  if (p.mode == 0) {
+    b0 = blockIdx.x / p.tiles_per_utt;
+    t0 = (blockIdx.x % p.tiles_per_utt) * TC_BM;
+    n0 = blockIdx.y * TC_BN;
+    num_k_iters = p.nseg * p.kb_per_seg;
+  } else {
+    t0 = blockIdx.x * TC_BM;                       // output-channel (row) tile of dW
+    const int i_tiles = (p.N + TC_BN - 1) / TC_BN;
+    seg_fixed = blockIdx.y / i_tiles;
+    n0 = (blockIdx.y % i_tiles) * TC_BN;
+    b_lo = blockIdx.z * p.utt_per_split;
+    int b_hi = min(p.Bt, b_lo + p.utt_per_split);
+    num_k_iters = max(0, b_hi - b_lo) * p.tb_per_utt;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[TC_STAGES + s]), 1); }
+    mbar_init(smem_u32(&bars[2 * TC_STAGES]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {                                 // 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                               // ===== TMA producer
+      for (int i = 0; i < num_k_iters; ++i) {
+        const int s = i % TC_STAGES, round = i / TC_STAGES;
+        mbar_wait(smem_u32(&bars[TC_STAGES + s]), (round & 1) ^ 1);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_expect_tx(full, TC_A_BYTES + TC_B_BYTES);
+        if (p.mode == 0) {
+          const int seg = i / p.kb_per_seg, kb = i % p.kb_per_seg;
+          tma_load_3d(smem_u32(sA + s * TC_A_BYTES), &mapA, full, seg * p.a_seg_col + kb * TC_BK, t0 + p.shift[seg], b0);
+          tma_load_3d(smem_u32(sB + s * TC_B_BYTES), &mapB, full, seg * p.b_seg_col + kb * TC_BK, n0, 0);
+        } else if (p.mode == 1) {
+          const int b = b_lo + i / p.tb_per_utt, tb = i % p.tb_per_utt;
+          tma_load_3d(smem_u32(sA + s * TC_A_BYTES), &mapA, full, tb * TC_BK, b, t0);
+          tma_load_3d(smem_u32(sB + s * TC_B_BYTES), &mapB, full, tb * TC_BK + p.shift[seg_fixed], b, n0);
+        } else {                                   // mode 2: [64 frames][64 channels] boxes, two per operand
+          const int b = b_lo + i / p.tb_per_utt, tk = (i % p.tb_per_utt) * TC_BK;
+          const uint32_t a = smem_u32(sA + s * TC_A_BYTES), bb = smem_u32(sB + s * TC_B_BYTES);
+          tma_load_3d(a, &mapA, full, t0, tk, b);
+          tma_load_3d(a + TC_A_BYTES / 2, &mapA, full, t0 + 64, tk, b);
+          tma_load_3d(bb, &mapB, full, n0, tk + p.shift[seg_fixed], b);
+          tma_load_3d(bb + TC_B_BYTES / 2, &mapB, full, n0 + 64, tk + p.shift[seg_fixed], b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                               // ===== MMA issuer
+      for (int i = 0; i < num_k_iters; ++i) {
+        const int s = i % TC_STAGES, round = i / TC_STAGES;
+        mbar_wait(smem_u32(&bars[s]), round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (p.mode != 2) {
+          const uint64_t da = make_sdesc(smem_u32(sA + s * TC_A_BYTES));
+          const uint64_t db = make_sdesc(smem_u32(sB + s * TC_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)     // 16 bf16 = 32 B per UMMA_K step inside the 128 B swizzle atom
+            umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kIdesc, (i | k) ? 1u : 0u);
+        } else {
+          const uint64_t da = make_sdesc(smem_u32(sA + s * TC_A_BYTES), TC_A_BYTES / 2);
+          const uint64_t db = make_sdesc(smem_u32(sB + s * TC_B_BYTES), TC_B_BYTES / 2);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)     // 16 k-rows = two 8-row groups = 2048 B per UMMA_K step
+            umma_f16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), kIdescMN, (i | k) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars[TC_STAGES + s]));          // frees this smem stage when the MMAs have read it
+      }
+      umma_commit(smem_u32(&bars[2 * TC_STAGES]));            // accumulator complete
+    }
+  } else {                                         // ===== epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // row of the 128-row tile held by this thread
+    if (num_k_iters > 0) {
+      mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    DropCtx dc = make_drop(p.drop);
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t r[32];
+      if (num_k_iters > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      const int nb = n0 + c * 32;
+      if (p.mode == 0) {
+        const int t = t0 + row;
+        const bool valid = t < p.T;
+        const long long m = (long long)b0 * p.T + t;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          const int n = nb + j;
+          if (p.bias && n < p.N) x += p.bias[n];
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (dc.p > 0.f && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j < p.N) {
+              const float4 mul = dropout_mul4(dc, ((unsigned long long)m * p.N + nb + j) >> 2);
+              v[j] *= mul.x; v[j + 1] *= mul.y; v[j + 2] *= mul.z; v[j + 3] *= mul.w;
+            }
+          }
+        }
+        if (valid) {
+          if (p.c_dtype == PKA_BF16) {
+            __nv_bfloat16* dst = (__nv_bfloat16*)p.C + m * p.ldc + nb;
+            if (nb + 32 <= p.N && (p.ldc & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                *reinterpret_cast<uint4*>(dst + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+            }
+          } else {
+            float* dst = (float*)p.C + m * p.ldc + nb;
+            if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+            }
+          }
+          if (p.Ct) {                              // transposed copy Ct[n, b, t]: lanes = consecutive t -> coalesced
+            __nv_bfloat16* dt = (__nv_bfloat16*)p.Ct + ((long long)b0 * p.Tp + t);
+            const long long pitch = (long long)p.Bt * p.Tp;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dt[(long long)(nb + j) * pitch] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      } else {                                     // mode 1: fp32 partial of dW rows (output channels)
+        const int o = t0 + row;
+        if (o < p.M) {
+          float* dst = (float*)p.C + ((long long)blockIdx.z * p.M + o) * p.ldc + (long long)seg_fixed * p.N + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
+// fixed-order sum of the split partials: out[m, n] (+)= sum_s ws[s][m][n]
+__global__ void tc_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long per, int splits, int accumulate) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < per; e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += ws[(long long)sp * per + e];
+    out[e] = accumulate ? out[e] + s : s;
+  }
+}
+
+// fp32 master weight W[N, nseg*K] -> bf16 copy (forward operand) and bf16 Wd[K, nseg*N] with Wd[i, s*N+o] = W[o, s*K+i]
+// (the data-gradient operand: K-major in the output-channel index)
+__global__ void weight_relayout_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wf,
+                                       __nv_bfloat16* __restrict__ Wd, int N, int K, int nseg) {
+  const long long total = (long long)N * nseg * K;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(e / ((long long)nseg * K));
+    const int rem = (int)(e % ((long long)nseg * K));
+    const int s = rem / K, i = rem % K;
+    const __nv_bfloat16 v = __float2bfloat16_rn(W[e]);
+    if (Wf) Wf[e] = v;
+    if (Wd) Wd[(long long)i * nseg * N + (long long)s * N + o] = v;
+  }
+}
+
+// dZ = (Y > 0) ? dY*scale : 0 in bf16, written row-major [rows, N] and transposed [N, Bt, Tp] (32x32 smem tiles)
+template <typename Tin>
+__global__ void relu_bwd_dual_kernel(const Tin* __restrict__ dY, const __nv_bfloat16* __restrict__ Y,
+                                     __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZt, int Bt, int T, int Tp,
+                                     int N, float scale, int gate) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, n = n0 + threadIdx.x;
+    float v = 0.f;
+    if (t < T && n < N) {
+      const long long idx = ((long long)b * T + t) * N + n;
+      v = to_f(dY[idx]);
+      if (gate) v = __bfloat162float(Y[idx]) > 0.f ? v * scale : 0.f;
+      if (dZ) dZ[idx] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dZt) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int n = n0 + i, t = t0 + threadIdx.x;
+      if (n < N && t < T) dZt[((long long)n * Bt + b) * Tp + t] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 3-D bf16 tensor map, innermost dim first; box = {64, box1, box2}; 128B swizzle; OOB elements read as zero
+static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                    uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who) {
+  EncodeTiledFn enc = get_encode();
+  PKA_REQUIRE(enc, PKA_EDEVICE, "%s: cuTensorMapEncodeTiled driver entry point not found", who);
+  PKA_REQUIRE(aligned16(base) && stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, PKA_EALIGN,
+              "%s: TMA needs 16-byte aligned base and strides (base %p, strides %llu, %llu)", who, base,
+              (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PKA_REQUIRE(r == CUDA_SUCCESS, PKA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (dims %llu,%llu,%llu)", who, (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+  return PKA_OK;
+}
+
+}  // namespace pka
+
+using namespace pka;
+
+extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
+  PKA_REQUIRE(d && d->A && d->B && d->C, PKA_EINVAL, "gemm_tc: null operand");
+  PKA_REQUIRE(d->Bt > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->nseg >= 1 && d->nseg <= PKA_MAX_CTX, PKA_EINVAL,
+              "gemm_tc: bad sizes Bt=%d T=%d N=%d K=%d nseg=%d", d->Bt, d->T, d->N, d->K, d->nseg);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_tc: cannot opt in to %d bytes of shared memory: %s", TC_SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  TcParams p;
+  p.mode = d->mode; p.Bt = d->Bt; p.T = d->T; p.N = d->N; p.K = d->K; p.nseg = d->nseg;
+  p.a_seg_col = d->a_seg_col; p.b_seg_col = d->b_seg_col;
+  for (int i = 0; i < PKA_MAX_CTX; ++i) p.shift[i] = d->shift[i];
+  p.C = d->C; p.Ct = d->Ct; p.ldc = d->ldc; p.c_dtype = d->c_dtype; p.Tp = d->Tp;
+  p.bias = d->bias; p.relu = d->relu; p.M = d->M; p.drop = d->drop;
+  p.kb_per_seg = (d->K + TC_BK - 1) / TC_BK;
+  p.tiles_per_utt = (d->T + TC_BM - 1) / TC_BM;
+  p.utt_per_split = 0; p.tb_per_utt = 0;
+  CUtensorMap mapA, mapB;
+  dim3 grid;
+  int rc;
+  if (d->mode == 0) {
+    PKA_REQUIRE(d->nseg == 1 || d->K % TC_BK == 0, PKA_EUNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d when nseg>1", d->K, TC_BK);
+    PKA_REQUIRE(d->drop.p == 0.f || d->N % 4 == 0, PKA_EUNSUPPORTED, "gemm_tc: dropout epilogue needs N%%4==0");
+    PKA_REQUIRE(!d->Ct || d->Tp >= d->T, PKA_EINVAL, "gemm_tc: Tp < T");
+    // A: [Bt, T, lda] bf16, visible width = a_seg_col*(nseg-1)+K columns; B: weights [N, ldb] with nseg K-segments
+    const uint64_t a_cols = (uint64_t)d->a_seg_col * (d->nseg - 1) + d->K;
+    rc = make_map(&mapA, d->A, a_cols, d->T, d->Bt, (uint64_t)d->lda * 2, (uint64_t)d->T * d->lda * 2, TC_BM, 1, "gemm_tc A");
+    if (rc) return rc;
+    const uint64_t b_cols = (uint64_t)d->b_seg_col * (d->nseg - 1) + d->K;
+    rc = make_map(&mapB, d->B, b_cols, d->N, 1, (uint64_t)d->ldb * 2, (uint64_t)d->N * d->ldb * 2, TC_BN, 1, "gemm_tc B");
+    if (rc) return rc;
+    grid = dim3(p.tiles_per_utt * d->Bt, (d->N + TC_BN - 1) / TC_BN, 1);
+  } else if (d->mode == 2) {
+    PKA_REQUIRE(d->M > 0 && d->splits >= 1, PKA_EINVAL, "gemm_tc wgrad: M=%d splits=%d", d->M, d->splits);
+    PKA_REQUIRE(d->c_dtype == PKA_F32, PKA_EUNSUPPORTED, "gemm_tc wgrad: partial sums are fp32");
+    // A = dZ [Bt, T, lda] (M = output channels contiguous), B = X [Bt, T, ldb] (N = input channels contiguous):
+    // MN-major operands, the reduction runs over frames; boxes are [64 frames][64 channels]
+    rc = make_map(&mapA, d->A, d->M, d->T, d->Bt, (uint64_t)d->lda * 2, (uint64_t)d->T * d->lda * 2, 64, 1, "gemm_tc dZ");
+    if (rc) return rc;
+    rc = make_map(&mapB, d->B, d->N, d->T, d->Bt, (uint64_t)d->ldb * 2, (uint64_t)d->T * d->ldb * 2, 64, 1, "gemm_tc X");
+    if (rc) return rc;
+    p.utt_per_split = (d->Bt + d->splits - 1) / d->splits;
+    p.tb_per_utt = (d->T + TC_BK - 1) / TC_BK;
+    grid = dim3((d->M + TC_BM - 1) / TC_BM, ((d->N + TC_BN - 1) / TC_BN) * d->nseg, d->splits);
+  } else {
+    PKA_REQUIRE(d->M > 0 && d->splits >= 1 && d->Tp >= d->T && d->Tp % 8 == 0, PKA_EINVAL, "gemm_tc wgrad: M=%d splits=%d Tp=%d", d->M, d->splits, d->Tp);
+    PKA_REQUIRE(d->c_dtype == PKA_F32, PKA_EUNSUPPORTED, "gemm_tc wgrad: partial sums are fp32");
+    // A = dZt [M, Bt, Tp], B = Xt [N, Bt, Tp]: dims {T, Bt, rows}, the box covers 64 frames of one utterance, 128 rows
+    rc = make_map(&mapA, d->A, d->T, d->Bt, d->M, (uint64_t)d->Tp * 2, (uint64_t)d->Bt * d->Tp * 2, 1, TC_BM, "gemm_tc dZt");
+    if (rc) return rc;
+    rc = make_map(&mapB, d->B, d->T, d->Bt, d->N, (uint64_t)d->Tp * 2, (uint64_t)d->Bt * d->Tp * 2, 1, TC_BN, "gemm_tc Xt");
+    if (rc) return rc;
+    p.utt_per_split = (d->Bt + d->splits - 1) / d->splits;
+    p.tb_per_utt = (d->T + TC_BK - 1) / TC_BK;
+    grid = dim3((d->M + TC_BM - 1) / TC_BM, ((d->N + TC_BN - 1) / TC_BN) * d->nseg, d->splits);
+  }
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(mapA, mapB, p);
+  return check_launch("gemm_tc");
+}
+
+extern "C" int pka_tc_reduce(const float* ws, float* out, int64_t per, int splits, int accumulate, void* stream) {
+  PKA_REQUIRE(ws && out && per > 0 && splits >= 1, PKA_EINVAL, "tc_reduce: bad arguments");
+  long long blocks = (per + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  tc_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(ws, out, per, splits, accumulate);
+  return check_launch("tc_reduce");
+}
+
+extern "C" int pka_weight_relayout(const float* W, void* Wf, void* Wd, int N, int K, int nseg, void* stream) {
+  PKA_REQUIRE(W && (Wf || Wd) && N > 0 && K > 0 && nseg >= 1, PKA_EINVAL, "weight_relayout: bad arguments");
+  const long long total = (long long)N * nseg * K;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  weight_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(W, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, N, K, nseg);
+  return check_launch("weight_relayout");
+}
+
+extern "C" int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, void* dZ, void* dZt, int Bt, int T, int Tp, int N,
+                                 float scale, int gate, void* stream) {
+  PKA_REQUIRE(dY && (dZ || dZt) && (!gate || Y), PKA_EINVAL, "relu_bwd_dual: null pointer");
+  PKA_REQUIRE(Bt > 0 && Bt <= 65535 && T > 0 && N > 0 && Tp >= T, PKA_EINVAL, "relu_bwd_dual: bad sizes");
+  dim3 grid((N + 31) / 32, (T + 31) / 32, Bt), block(32, 8);
+  if (dy_dtype == PKA_BF16)
+    relu_bwd_dual_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
+  else if (dy_dtype == PKA_F32)
+    relu_bwd_dual_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "relu_bwd_dual: dtype %d", dy_dtype);
+  return check_launch("relu_bwd_dual");
+}

@@ -97,7 +97,7 @@ class BeamDecoder:
         self.n_not_done.fill_(self.n_utt)
         self.src_mask.copy_(src_pad_mask.to(torch.uint8))
         with torch.no_grad():
-            enc = self.dec.enc_dec_projection(enc_output)                      # [n_utt, T, Dd], once (T/Models.py:199)
+            enc = self.dec.enc_dec_projection(enc_output, out_fp32=True)                      # [n_utt, T, Dd], once (T/Models.py:199)
             for l, layer in enumerate(self.dec.layer_stack):
                 self.enc_kv[l].copy_(ops.head_proj(enc, layer.enc_attn.w_ks, layer.enc_attn.w_vs))
         self.steps_run = 0

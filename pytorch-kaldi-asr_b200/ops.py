@@ -496,3 +496,128 @@ def dropout_keep_mask(n: int, drop: Drop, device) -> torch.Tensor:
     keep = torch.empty(n, device=device, dtype=torch.uint8)
     L.check(L.lib().pka_dropout_mask(L.ptr(keep), C.c_int64(n), C.byref(drop.c()), L.stream_ptr()), "dropout_mask")
     return keep
+
+
+# ================================================================================================ bf16 tensor-core path
+def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col=0, shift=(), bias=None, relu=False,
+                 drop: Optional[Drop] = None, out_dtype=torch.bfloat16):
+    """mode 0 of pka_gemm_tc: C[b,t,:] = epi(sum_seg A[b,t+shift[seg],:] . Bw[:, seg]^T) -> C [Bt,T,N]."""
+    L.require_cuda(A, Bw, bias)
+    assert A.dtype == torch.bfloat16 and Bw.dtype == torch.bfloat16
+    Cout = torch.empty(Bt, T, N, device=A.device, dtype=out_dtype)
+    d = L.TcDesc()
+    d.A, d.B, d.C, d.Ct = A.data_ptr(), Bw.data_ptr(), Cout.data_ptr(), 0
+    d.bias = bias.data_ptr() if bias is not None else 0
+    d.mode, d.Bt, d.T, d.Tp, d.M, d.N, d.K, d.nseg = 0, Bt, T, 0, 0, N, K, nseg
+    d.lda, d.ldb, d.ldc = lda, ldb, N
+    d.a_seg_col, d.b_seg_col = a_seg_col, b_seg_col
+    for i, sft in enumerate(shift):
+        d.shift[i] = int(sft)
+    d.relu, d.c_dtype, d.splits = int(relu), L.dtype_code(Cout), 1
+    d.drop = _cdrop(drop)
+    L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc")
+    return Cout
+
+
+def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None):
+    """mode 2: dW[o, seg*N+i] = sum_{b,t} dZ[b,t,o] * X[b,t+shift[seg],i] -> fp32 [M, nseg*N], straight from the row-major
+    activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
+    split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic)."""
+    assert dZ.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dZ.is_contiguous() and X.is_contiguous()
+    tiles = ((M + 127) // 128) * ((N + 127) // 128) * nseg
+    splits = max(1, min(Bt, 148 // max(1, tiles)))
+    ws = torch.empty(splits, M, nseg * N, device=dZ.device, dtype=torch.float32)
+    d = L.TcDesc()
+    d.A, d.B, d.C, d.Ct, d.bias = dZ.data_ptr(), X.data_ptr(), ws.data_ptr(), 0, 0
+    d.mode, d.Bt, d.T, d.Tp, d.M, d.N, d.K, d.nseg = 2, Bt, T, 0, M, N, T, nseg
+    d.lda, d.ldb, d.ldc = M, N, nseg * N
+    for i, sft in enumerate(shift):
+        d.shift[i] = int(sft)
+    d.relu, d.c_dtype, d.splits = 0, L.PKA_F32, splits
+    d.drop = L.NO_DROPOUT
+    L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
+    acc = out is not None
+    if out is None:
+        out = torch.empty(M, nseg * N, device=dZ.device, dtype=torch.float32)
+    L.check(L.lib().pka_tc_reduce(L.ptr(ws), L.ptr(out), C.c_int64(M * nseg * N), splits, int(acc), L.stream_ptr()), "tc_reduce")
+    return out
+
+
+def gate_to_bf16(x, Bt, T, N, y=None, scale=1.0):
+    """bf16 [Bt,T,N] copy of x (fp32 or bf16); with `y` applies the ReLU+dropout gate (y > 0 ? x*scale : 0)."""
+    L.require_cuda(x, y)
+    x = x.contiguous()
+    out = torch.empty(Bt, T, N, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().pka_relu_bwd_dual(L.ptr(x), L.dtype_code(x), L.ptr(y), L.ptr(out), C.c_void_p(0), Bt, T, (T + 7) // 8 * 8,
+                                      N, C.c_float(scale), int(y is not None), L.stream_ptr()), "relu_bwd_dual")
+    return out
+
+
+def weight_relayout(w2, K, nseg, want_f=True, want_d=True):
+    N = w2.shape[0]
+    wf = torch.empty(N, nseg * K, device=w2.device, dtype=torch.bfloat16) if want_f else None
+    wd = torch.empty(K, nseg * N, device=w2.device, dtype=torch.bfloat16) if want_d else None
+    L.check(L.lib().pka_weight_relayout(L.ptr(w2), L.ptr(wf), L.ptr(wd), N, K, nseg, L.stream_ptr()), "weight_relayout")
+    return wf, wd
+
+
+class _LinearTcFn(torch.autograd.Function):
+    """bf16 tensor-core version of _LinearFn for [Bt,T,K] activations (tcgen05 forward, data-gradient and
+    weight-gradient).  Weights stay fp32 masters; their bf16 operand copies are made here, once per call."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, splice, relu, drop, out_fp32):
+        L.require_cuda(x, weight, bias)
+        assert x.dtype == torch.bfloat16 and x.dim() == 3 and x.is_contiguous()
+        Bt, T, kin = x.shape
+        n_ctx = len(splice) if splice else 1
+        w2 = weight.reshape(weight.shape[0], -1)
+        N = w2.shape[0]
+        assert w2.shape[1] == n_ctx * kin
+        needs_dx = ctx.needs_input_grad[0]
+        wf, wd = weight_relayout(w2.detach(), kin, n_ctx, True, needs_dx)
+        y = gemm_tc_rows(x, wf, Bt, T, N, kin, nseg=n_ctx, lda=kin, ldb=n_ctx * kin, b_seg_col=kin, shift=splice or (),
+                         bias=bias, relu=relu, drop=drop, out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        ctx.save_for_backward(x, wd, y if relu else None)
+        ctx.meta = (Bt, T, kin, N, n_ctx, tuple(splice) if splice else (0,), relu, drop, bias is not None, weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wd, y = ctx.saved_tensors
+        Bt, T, kin, N, n_ctx, splice, relu, drop, has_bias, wshape = ctx.meta
+        dy = dy.contiguous()
+        use_drop = drop is not None and drop.on
+        if relu:
+            assert y.dtype == torch.bfloat16
+            dz = gate_to_bf16(dy, Bt, T, N, y=y, scale=(1.0 / (1.0 - drop.p)) if use_drop else 1.0)
+        else:
+            if use_drop:
+                tmp = torch.empty_like(dy)
+                L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(tmp), L.dtype_code(dy), C.c_int64(dy.numel()),
+                                                _byref_drop(drop), L.stream_ptr()), "dropout_bwd")
+                dy = tmp
+            dz = dy if dy.dtype == torch.bfloat16 else gate_to_bf16(dy, Bt, T, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tc_rows(dz, wd, Bt, T, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * N, b_seg_col=N,
+                              shift=[-c for c in splice])
+        if ctx.needs_input_grad[1]:
+            dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice).view(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dz.view(Bt * T, N))
+        return dx, dw, db, None, None, None, None
+
+
+def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32=False):
+    return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32)
+
+
+def affine_tc(x, weight_kn, bias=None):
+    """Frozen LDA affine on the tensor cores: x bf16 [Bt,T,K] @ W[K,N] + b -> bf16.  No autograd."""
+    Bt, T, K = x.shape
+    N = weight_kn.shape[1]
+    wt = torch.empty(N, K, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().pka_transpose(L.ptr(weight_kn.detach().contiguous()), L.PKA_F32, L.ptr(wt), L.PKA_BF16, K, N, L.stream_ptr()),
+            "transpose")
+    return gemm_tc_rows(x.detach(), wt, Bt, T, N, K, lda=K, ldb=K, bias=bias.detach() if bias is not None else None)

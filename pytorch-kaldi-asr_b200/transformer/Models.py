@@ -123,7 +123,9 @@ class EncoderTest(nn.Module):
         if cmvn:
             assert src_pad_mask is not None, "CMVN needs the pad mask to know the utterance lengths"
             lengths = src_pad_mask.to(torch.int32).sum(dim=1, dtype=torch.int32)
-        x = ops.frontend(src_seq, lengths, fold, self.concat.index, cmvn)
+        bf16 = ops.compute_mode() == "bf16"     # activations of the TDNN stack live in HBM as bf16, GEMMs on tcgen05
+        x = ops.frontend(src_seq, lengths, fold, self.concat.index, cmvn,
+                         out_dtype=torch.bfloat16 if bf16 else torch.float32)
         x = self.lda_layer(x)
         x = self.src_projection(x, drop=self._rng.make(self.p, self._site_src, dev, self.training))
         for layer in self.tdnn_stack:
@@ -154,7 +156,7 @@ class Decoder(nn.Module):
 
     def forward(self, tgt_seq, tgt_pad_mask, src_pad_mask, enc_output, return_attns=False):
         dev = enc_output.device
-        enc = self.enc_dec_projection(enc_output)
+        enc = self.enc_dec_projection(enc_output, out_fp32=True)       # bf16 encoder output -> fp32 decoder
         x = ops.embed_pos(tgt_seq, self.tgt_word_emb.weight, self.position_enc.weight,
                           self._rng.make(self.p, self._site_emb, dev, self.training), constants.PAD)
         slf_mask = get_attn_padding_mask(tgt_pad_mask, tgt_pad_mask) + get_attn_subsequent_mask(tgt_pad_mask, *self.sub)

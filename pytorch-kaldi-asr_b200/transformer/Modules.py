@@ -20,7 +20,10 @@ class Linear(nn.Module):
         self.linear = nn.Linear(d_in, d_out, bias=bias)
         init.xavier_normal_(self.linear.weight)
 
-    def forward(self, x, drop=None, residual=None):
+    def forward(self, x, drop=None, residual=None, out_fp32=False):
+        if x.dtype == torch.bfloat16:          # bf16 training path: tcgen05 GEMMs (ops.set_compute_mode("bf16"))
+            assert residual is None
+            return ops.linear_tc(x, self.linear.weight, self.linear.bias, drop=drop, out_fp32=out_fp32)
         return ops.linear(x, self.linear.weight, self.linear.bias, drop=drop, residual=residual)
 
 

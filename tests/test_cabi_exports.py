@@ -27,7 +27,7 @@ def library():
 
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
-    for must in ("pka_frontend_fwd", "pka_gemm_f32", "pka_gemm_bf16_tc", "pka_attn_fwd", "pka_attn_bwd",
+    for must in ("pka_frontend_fwd", "pka_gemm_f32", "pka_gemm_tc", "pka_attn_fwd", "pka_attn_bwd",
                  "pka_add_layernorm_fwd", "pka_add_layernorm_bwd", "pka_ce_fwd", "pka_ce_bwd", "pka_beam_advance",
                  "pka_tree_attn", "pka_adam_step", "pka_last_error"):
         assert must in syms

@@ -1,0 +1,105 @@
+"""bf16 tensor-core path (tcgen05 / TMEM / TMA) parity on the B200 (`-m gpu`).
+
+Stated bf16 tolerances: GEMM outputs within 1e-2 of the tensor scale (bf16 storage rounds at 2^-9);
+whole model: logits within 2e-2 of the logit scale, loss within 1e-2 relative, per-tensor gradient cosine >= 0.999."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import acoustic_model as am          # noqa: E402
+from oracle import train_step as otrain          # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-6))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize("Bt,T,kin,N,ctx,relu,bias", [
+    (1, 128, 64, 128, None, False, False),
+    (3, 77, 200, 256, None, False, False),       # src_projection: K not a multiple of 64 (TMA zero-fills the tail)
+    (2, 50, 128, 53, None, False, False),        # N tail
+    (4, 499, 256, 256, [-3, 0, 3], True, True),  # TDNN layer at TIMIT size, splice by shifted TMA boxes
+    (5, 130, 256, 256, [-1, 0, 1], True, True),
+    (2, 300, 256, 128, None, False, False),      # enc_dec_projection
+])
+def test_linear_tc_fwd_bwd(Bt, T, kin, N, ctx, relu, bias):
+    from pytorch_kaldi_asr_b200 import ops
+    n = len(ctx) if ctx else 1
+    x = rnd(Bt, T, kin, seed=1).bfloat16()
+    w = rnd(N, n * kin, seed=2, scale=1.0 / math.sqrt(n * kin))
+    b = rnd(N, seed=3, scale=0.1) if bias else None
+    gy = rnd(Bt, T, N, seed=4).bfloat16()
+    xg = x.to(DEV).requires_grad_(True)
+    wg = w.to(DEV).requires_grad_(True)
+    bg = b.to(DEV).requires_grad_(True) if bias else None
+    out = ops.linear_tc(xg, wg, bg, splice=ctx, relu=relu)
+    out.backward(gy.to(DEV))
+    # reference on the bf16-rounded operands the kernel actually multiplies
+    xr = x.float().requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    ref = F.linear(am.splice(xr, ctx) if ctx else xr, wr, br)
+    if relu:
+        ref = ref * (out.detach().float().cpu() > 0)
+    ref.backward(gy.float())
+    assert rel_err(out, ref) <= 1e-2
+    assert rel_err(xg.grad, xr.grad) <= 1e-2
+    assert rel_err(wg.grad, wr.grad) <= 1e-2
+    if bias:
+        assert rel_err(bg.grad, br.grad) <= 1e-2
+
+
+def test_linear_tc_fp32_output_and_dropout_mask():
+    from pytorch_kaldi_asr_b200 import ops
+    Bt, T, kin, N, p = 2, 140, 200, 256, 0.35
+    x = rnd(Bt, T, kin, seed=1).bfloat16()
+    w = rnd(N, kin, seed=2, scale=0.1)
+    drop = ops.Drop(p, 3, 77, torch.tensor([4], dtype=torch.int64, device=DEV))
+    keep = ops.dropout_keep_mask(Bt * T * N, drop, DEV).cpu().view(Bt, T, N).float()
+    out = ops.linear_tc(x.to(DEV), w.to(DEV), None, drop=drop, out_fp32=True)
+    assert out.dtype == torch.float32
+    ref = F.linear(x.float(), w.bfloat16().float()) * keep / (1 - p)
+    assert rel_err(out, ref) <= 1e-5          # fp32 accumulation in TMEM, fp32 store: only summation order differs
+
+
+def cosine(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def test_whole_model_bf16_vs_oracle():
+    import pytorch_kaldi_asr_b200 as pk
+    from pytorch_kaldi_asr_b200.utils import synthetic
+    cfg = am.example_config(en_dropout=0.0, de_dropout=0.0)
+    lda = synthetic.lda_matrix()
+    sd = am.init_state_dict(cfg, lda, seed=0)
+    batch = synthetic.batches(1, 6, seed=1234)[0]
+    logits_ref, loss_ref, _, _, grads_ref = otrain.loss_and_grads(sd, cfg, batch[1:], smoothing=False)
+    model = pk.Transformer(lda_mat=lda, **{k: v for k, v in cfg.items() if k != "encoder_type"})
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    pk.set_compute_mode("bf16")
+    try:
+        src, smask, tgt, tmask = pk.train._to_device(batch, DEV)
+        pred = model(src, smask, tgt[:, :-1], tmask[:, :-1])
+        loss, _ = pk.get_performance(None, pred, tgt[:, 1:], smoothing=False)
+        loss.backward()
+    finally:
+        pk.set_compute_mode("fp32")
+    assert pred.dtype == torch.float32
+    assert rel_err(pred, logits_ref) <= 2e-2
+    assert abs(float(loss) - float(loss_ref)) <= 1e-2 * abs(float(loss_ref))
+    worst = min(cosine(p.grad, grads_ref[k]) for k, p in model.named_parameters() if k in grads_ref)
+    assert worst >= 0.999, "worst gradient cosine %.5f" % worst
