@@ -119,6 +119,13 @@ int pka_gemm_tc(const pka_tc_desc* d, void* stream);
 int pka_tc_reduce(const float* ws, float* out, int64_t per, int splits, int accumulate, void* stream);
 /* fp32 W[N, nseg*K] -> Wf bf16 (same layout, forward operand) and/or Wd bf16 [K, nseg*N], Wd[i, s*N+o] = W[o, s*K+i] */
 int pka_weight_relayout(const float* W, void* Wf, void* Wd, int N, int K, int nseg, void* stream);
+/* per-head projection weights w_p[H,D,dk], p < P <= 3 (T/SubLayers.py:29-31) -> packed bf16 GEMM operands
+ * Wf[(p*H+h)*dk+j, d] (forward) and Wd[d, (p*H+h)*dk+j] (data-gradient); and the way back for the weight gradient
+ * dWcat fp32 [(p,h,j), d] -> g_p[h,d,j]. */
+int pka_head_weight_relayout(const float* w0, const float* w1, const float* w2, int P, int H, int D, int dk, void* Wf,
+                             void* Wd, void* stream);
+int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, float* g2, int P, int H, int D, int dk,
+                           void* stream);
 /* dZ = gate ? ((Y > 0) ? dY*scale : 0) : dY, bf16, written row-major [Bt*T, N] (dZ) and transposed [N, Bt, Tp] (dZt) */
 int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, void* dZ, void* dZt, int Bt, int T, int Tp, int N,
                       float scale, int gate, void* stream);

@@ -58,24 +58,46 @@ __global__ void embed_pos_fwd_kernel(const long long* __restrict__ tok, const fl
   }
 }
 
-// one CTA per vocabulary row: scan all tokens in order, accumulate matching rows -> deterministic scatter-add
+// one CTA per vocabulary row.  Warp 0 compacts the positions holding this token (ballot + popc, ascending order), then
+// every thread owns one column and sums the matching rows in that fixed order -> deterministic scatter-add, and the
+// D-wide work is only done for the ~n_tok/V matching rows instead of all of them.
+constexpr int kEmbChunk = 4096;
 template <typename T>
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __restrict__ dout,
                                  float* __restrict__ demb, long long n_tok, int D, int padding_idx,
                                  const pka_dropout drop) {
+  __shared__ int match[kEmbChunk];
+  __shared__ int n_match;
   const int v = blockIdx.x;
   if (v == padding_idx) return;
   DropCtx dc = make_drop(drop);
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = 0; r < n_tok; ++r) {
-      if (tok[r] == v) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < n_tok; base += kEmbChunk) {
+    const int n = (int)((n_tok - base) < kEmbChunk ? (n_tok - base) : kEmbChunk);
+    if (warp == 0) {
+      int cnt = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const bool hit = i < n && tok[base + i] == v;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) match[cnt + __popc(m & ((1u << lane) - 1u))] = i;
+        cnt += __popc(m);
+      }
+      if (lane == 0) n_match = cnt;
+    }
+    __syncthreads();
+    const int nm = n_match;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < nm; ++k) {
+        const long long r = base + match[k];
         float g = to_f(dout[r * D + c]);
         if (dc.p > 0.f) g = dropout_keep(dc, (unsigned long long)(r * D + c)) ? g * dc.scale : 0.f;
         acc += g;
       }
+      if (nm) demb[(long long)v * D + c] += acc;
     }
-    demb[(long long)v * D + c] += acc;
+    __syncthreads();
   }
 }
 

@@ -305,6 +305,34 @@ __global__ void weight_relayout_kernel(const float* __restrict__ W, __nv_bfloat1
   }
 }
 
+// per-head projection weights w_p[H, D, dk] (p < P, reference layout T/SubLayers.py:29-31) <-> the packed operands of the
+// tensor-core GEMMs: Wf[(p*H+h)*dk + j, d] (forward, K-major in d) and Wd[d, (p*H+h)*dk + j] (data-gradient), bf16.
+struct HeadPtrs { const float* w[3]; float* g[3]; };
+__global__ void head_weight_relayout_kernel(HeadPtrs hp, __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd,
+                                            int P, int H, int D, int dk) {
+  const long long per = (long long)H * D * dk, total = per * P;
+  const int ntot = P * H * dk;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int pidx = (int)(e / per);
+    const long long r = e % per;
+    const int h = (int)(r / ((long long)D * dk)), d = (int)((r / dk) % D), j = (int)(r % dk);
+    const __nv_bfloat16 v = __float2bfloat16_rn(hp.w[pidx][r]);
+    const int n = (pidx * H + h) * dk + j;
+    if (Wf) Wf[(long long)n * D + d] = v;
+    if (Wd) Wd[(long long)d * ntot + n] = v;
+  }
+}
+// dWcat fp32 [(p,h,j), d] -> dw_p[h, d, j]
+__global__ void head_grad_relayout_kernel(HeadPtrs hp, const float* __restrict__ dWcat, int P, int H, int D, int dk) {
+  const long long per = (long long)H * D * dk, total = per * P;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int pidx = (int)(e / per);
+    const long long r = e % per;
+    const int h = (int)(r / ((long long)D * dk)), d = (int)((r / dk) % D), j = (int)(r % dk);
+    if (hp.g[pidx]) hp.g[pidx][r] = dWcat[(long long)((pidx * H + h) * dk + j) * D + d];
+  }
+}
+
 // dZ = (Y > 0) ? dY*scale : 0 in bf16, written row-major [rows, N] and transposed [N, Bt, Tp] (32x32 smem tiles)
 template <typename Tin>
 __global__ void relu_bwd_dual_kernel(const Tin* __restrict__ dY, const __nv_bfloat16* __restrict__ Y,
@@ -350,6 +378,15 @@ static EncodeTiledFn get_encode() {
 // 3-D bf16 tensor map, innermost dim first; box = {64, box1, box2}; 128B swizzle; OOB elements read as zero
 static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                     uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who) {
+  // cuTensorMapEncodeTiled is a driver call and needs a current context in THIS thread.  Autograd worker threads may
+  // not have one bound yet when their first call into the library is a tensor-core GEMM, so make the (statically
+  // linked) runtime bind the primary context first -- with a call that is legal during stream capture.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaStreamCaptureStatus cs;
+    cudaStreamIsCapturing(cudaStreamPerThread, &cs);
+    ctx_bound = true;
+  }
   EncodeTiledFn enc = get_encode();
   PKA_REQUIRE(enc, PKA_EDEVICE, "%s: cuTensorMapEncodeTiled driver entry point not found", who);
   PKA_REQUIRE(aligned16(base) && stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, PKA_EALIGN,
@@ -461,4 +498,26 @@ extern "C" int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, vo
     relu_bwd_dual_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "relu_bwd_dual: dtype %d", dy_dtype);
   return check_launch("relu_bwd_dual");
+}
+
+extern "C" int pka_head_weight_relayout(const float* w0, const float* w1, const float* w2, int P, int H, int D, int dk,
+                                        void* Wf, void* Wd, void* stream) {
+  PKA_REQUIRE(w0 && P >= 1 && P <= 3 && (P < 2 || w1) && (P < 3 || w2) && (Wf || Wd), PKA_EINVAL, "head_weight_relayout: bad arguments");
+  HeadPtrs hp; hp.w[0] = w0; hp.w[1] = w1; hp.w[2] = w2; hp.g[0] = hp.g[1] = hp.g[2] = nullptr;
+  const long long total = (long long)P * H * D * dk;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  head_weight_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(hp, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, P, H, D, dk);
+  return check_launch("head_weight_relayout");
+}
+
+extern "C" int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, float* g2, int P, int H, int D, int dk,
+                                      void* stream) {
+  PKA_REQUIRE(dWcat && P >= 1 && P <= 3, PKA_EINVAL, "head_grad_relayout: bad arguments");
+  HeadPtrs hp; hp.w[0] = hp.w[1] = hp.w[2] = nullptr; hp.g[0] = g0; hp.g[1] = g1; hp.g[2] = g2;
+  const long long total = (long long)P * H * D * dk;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  head_grad_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(hp, dWcat, P, H, D, dk);
+  return check_launch("head_grad_relayout");
 }

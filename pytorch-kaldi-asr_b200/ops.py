@@ -222,6 +222,9 @@ class _HeadProjFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, *ws):
         L.require_cuda(x, *ws)
+        if x.dtype == torch.bfloat16:
+            return _HeadProjFn._forward_tc(ctx, x, ws)
+        ctx.tc = False
         lead, D = x.shape[:-1], x.shape[-1]
         x2 = x.reshape(-1, D)
         if not x2.is_contiguous():
@@ -239,7 +242,48 @@ class _HeadProjFn(torch.autograd.Function):
         return out.view(*lead, P * H * dk)
 
     @staticmethod
+    def _forward_tc(ctx, x, ws):
+        """bf16 x [Bt,T,D] (the encoder memory for cross-attention K/V): one tcgen05 GEMM for all P*H heads, fp32 out."""
+        assert x.dim() == 3 and x.is_contiguous()
+        Bt, T, D = x.shape
+        H, _, dk = ws[0].shape
+        P = len(ws)
+        ntot = P * H * dk
+        needs_dx = ctx.needs_input_grad[0]
+        wf = torch.empty(ntot, D, device=x.device, dtype=torch.bfloat16)
+        wd = torch.empty(D, ntot, device=x.device, dtype=torch.bfloat16) if needs_dx else None
+        wp = [L.ptr(w.detach()) for w in ws] + [C.c_void_p(0)] * (3 - P)
+        L.check(L.lib().pka_head_weight_relayout(wp[0], wp[1], wp[2], P, H, D, dk, L.ptr(wf), L.ptr(wd), L.stream_ptr()),
+                "head_weight_relayout")
+        out = gemm_tc_rows(x, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.float32)
+        ctx.tc = True
+        ctx.save_for_backward(x, wd)
+        ctx.meta = (Bt, T, D, H, dk, P)
+        return out
+
+    @staticmethod
+    def _backward_tc(ctx, dy):
+        x, wd = ctx.saved_tensors
+        Bt, T, D, H, dk, P = ctx.meta
+        ntot = P * H * dk
+        dz = gate_to_bf16(dy, Bt, T, ntot)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot)
+        dws = [None] * P
+        if any(ctx.needs_input_grad[1:1 + P]):
+            dwcat = gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,))
+            dws = [torch.empty(H, D, dk, device=x.device, dtype=torch.float32) if ctx.needs_input_grad[1 + p] else None
+                   for p in range(P)]
+            gp = [L.ptr(g) for g in dws] + [C.c_void_p(0)] * (3 - P)
+            L.check(L.lib().pka_head_grad_relayout(L.ptr(dwcat), gp[0], gp[1], gp[2], P, H, D, dk, L.stream_ptr()),
+                    "head_grad_relayout")
+        return (dx, *dws)
+
+    @staticmethod
     def backward(ctx, dy):
+        if ctx.tc:
+            return _HeadProjFn._backward_tc(ctx, dy)
         x2, *ws = ctx.saved_tensors
         lead, D, H, dk, P = ctx.meta
         M = x2.shape[0]

@@ -156,7 +156,9 @@ class Decoder(nn.Module):
 
     def forward(self, tgt_seq, tgt_pad_mask, src_pad_mask, enc_output, return_attns=False):
         dev = enc_output.device
-        enc = self.enc_dec_projection(enc_output, out_fp32=True)       # bf16 encoder output -> fp32 decoder
+        # bf16 mode: the projected encoder memory stays bf16 -- its only consumers are the cross-attention K/V
+        # projections (the largest decoder GEMMs: all T frames, every layer), which then run on the tensor cores too
+        enc = self.enc_dec_projection(enc_output, out_fp32=(ops.compute_mode() != "bf16"))
         x = ops.embed_pos(tgt_seq, self.tgt_word_emb.weight, self.position_enc.weight,
                           self._rng.make(self.p, self._site_emb, dev, self.training), constants.PAD)
         slf_mask = get_attn_padding_mask(tgt_pad_mask, tgt_pad_mask) + get_attn_subsequent_mask(tgt_pad_mask, *self.sub)
