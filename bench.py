@@ -152,28 +152,56 @@ def time_kernel(fn, iters=20, warm=3):
     return s.elapsed_time(e) / iters * 1e-3          # seconds per launch
 
 
-def roofline_probe(model, B, T, pk):
+def roofline_probe(model, B, T, pk, mode):
     """Dominant kernel of the step = the TDNN GEMM family (6 forward + 6 dgrad + 6 wgrad launches, ~85 % of the FLOPs).
-    Timed alone with CUDA events on the launching stream at the step's real shape [B*T, 768] x [768, 256]."""
+    Timed alone with CUDA events on the launching stream at the step's real shape [B*T, 768] x [768, 256];
+    algorithmic FLOPs per launch = 2 * B*T * 768 * 256 (padded frames included: the reference computes them too)."""
     from pytorch_kaldi_asr_b200 import ops
     layer = model.encoder_test.tdnn_stack[2]
-    x = torch.randn(B, T, 256, device="cuda")
-    # rotate over enough input copies to exceed L2 (126 MB): 14 MB per copy -> 12 copies
-    xs = [x.clone() for _ in range(12)]
-    i = [0]
-
-    def fwd():
-        with torch.no_grad():
-            ops.linear(xs[i[0] % 12], layer.proj.weight, layer.proj.bias, splice=layer.concat.index, relu=True)
-        i[0] += 1
-
-    sec = time_kernel(fwd)
+    ctx = layer.concat.index
     flops = 2.0 * B * T * 768 * 256
     pk_ = peaks()
+    out = {}
+    if mode == "bf16":
+        xs = [torch.randn(B, T, 256, device="cuda").bfloat16() for _ in range(24)]          # 24 x 8 MB > 126 MB L2
+        dzs = [torch.randn(B, T, 256, device="cuda").bfloat16() for _ in range(24)]
+        wf, wd = ops.weight_relayout(layer.proj.weight.detach(), 256, 3)
+        bias = layer.proj.bias.detach()
+        i = [0]
+
+        def fwd():
+            i[0] += 1
+            ops.gemm_tc_rows(xs[i[0] % 24], wf, B, T, 256, 256, nseg=3, lda=256, ldb=768, b_seg_col=256, shift=ctx, bias=bias, relu=True)
+
+        def dgrad():
+            i[0] += 1
+            ops.gemm_tc_rows(dzs[i[0] % 24], wd, B, T, 256, 256, nseg=3, lda=256, ldb=768, b_seg_col=256, shift=[-c for c in ctx])
+
+        def wgrad():
+            i[0] += 1
+            ops.gemm_tc_wgrad(dzs[i[0] % 24], xs[i[0] % 24], B, T, 256, 256, 3, ctx)
+
+        secs = {"fwd": time_kernel(fwd), "dgrad": time_kernel(dgrad), "wgrad": time_kernel(wgrad)}
+        sec = secs["fwd"]
+        out["kernel"] = "gemm_tc_kernel (tcgen05.mma 128x128x16, TMEM accumulators, TMA 128B-swizzle, spliced TDNN forward)"
+        out["family_us"] = {k: v * 1e6 for k, v in secs.items()}
+        out["family_tflops"] = {k: flops / v / 1e12 for k, v in secs.items()}
+    else:
+        xs = [torch.randn(B, T, 256, device="cuda") for _ in range(12)]
+        i = [0]
+
+        def fwd():
+            with torch.no_grad():
+                ops.linear(xs[i[0] % 12], layer.proj.weight, layer.proj.bias, splice=ctx, relu=True)
+            i[0] += 1
+
+        sec = time_kernel(fwd)
+        out["kernel"] = "gemm_f32_kernel<128,128,32,8,8> (TDNN splice+Linear+bias+ReLU, fp32 SIMT exact path)"
     achieved = flops / sec / 1e12
-    return {"bound": "tensor", "kernel": "gemm_f32_kernel<128,128,32,8,8> (TDNN splice+Linear+bias+ReLU, fp32 SIMT exact path)",
-            "achieved": achieved, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk_["bf16_tflops"],
-            "traffic": None, "peak_source": pk_["source"] + " bf16 burst", "us_per_launch": sec * 1e6}
+    out.update({"bound": "tensor", "achieved": achieved, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk_["bf16_tflops"], "traffic": None, "peak_source": pk_["source"] + " bf16 burst",
+                "us_per_launch": sec * 1e6, "flops_per_launch": flops})
+    return out
 
 
 def hbm_probe():
@@ -192,6 +220,51 @@ def hbm_probe():
     gbs = 3.0 * rows * D * 4 / sec / 1e9
     return {"kernel": "add_ln_fwd_kernel", "achieved": gbs, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk_["hbm_gbs"],
             "bytes_per_launch": 3 * rows * D * 4}
+
+
+def decode_bench(model, pk, rank, world, n_total=1000, batch=125, beam=10, max_len=100):
+    """BASELINE config 4: beam-10 decoding of 1000 synthetic utterances, sharded over the ranks with no collective.
+    fp32 exact path.  Returns per-rank (seconds_forced, seconds_natural, n_utts, steps_natural)."""
+    import types
+    from pytorch_kaldi_asr_b200 import parallel
+    from pytorch_kaldi_asr_b200.decode import translate_batch
+    from pytorch_kaldi_asr_b200.utils import synthetic
+    from pytorch_kaldi_asr_b200.utils.instances_handler import pad_to_longest
+    pk.set_compute_mode("fp32")
+    feats, _ = synthetic.utterances(n_total, np.random.RandomState(4321))
+    lo, hi = parallel.shard_range(n_total, rank, world)
+    mine = feats[lo:hi]
+    mine.sort(key=lambda f: len(f))                               # length-sorted batches waste less padding
+    batches = []
+    for i in range(0, len(mine), batch):
+        src, mask = pad_to_longest(mine[i:i + batch])
+        batches.append((None, torch.from_numpy(src).pin_memory(), torch.from_numpy(mask).pin_memory(), None, None))
+    out = {}
+    for forced in (True, False):
+        opt = types.SimpleNamespace(use_gpu=True, beam_size=beam, max_token_seq_len=max_len, nbest=1, force_full_length=forced)
+        translate_batch(model, batches[0], opt, None)             # warm-up: buffers + step graph for the first shape
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in batches:
+            translate_batch(model, b, opt, None)                  # ends with the D2H read-out of the lattices
+        torch.cuda.synchronize()
+        out["forced" if forced else "natural"] = time.perf_counter() - t0
+    return out, hi - lo
+
+
+def cpu_decode_baseline(n_utt, beam, max_len, threads):
+    from oracle import acoustic_model as am
+    from oracle import beam_decode as obd
+    from pytorch_kaldi_asr_b200.utils import synthetic
+    from pytorch_kaldi_asr_b200.utils.instances_handler import pad_to_longest
+    torch.set_num_threads(threads)
+    cfg = am.example_config()
+    sd = am.init_state_dict(cfg, synthetic.lda_matrix(), seed=0)
+    feats, _ = synthetic.utterances(n_utt, np.random.RandomState(4321))
+    src, mask = pad_to_longest(feats)
+    t0 = time.perf_counter()
+    obd.translate_batch(sd, cfg, src, mask, beam, max_len, 1, force_full_length=True)
+    return n_utt / (time.perf_counter() - t0)
 
 
 def run_b200(args):
@@ -306,6 +379,16 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, frames_e2e, _ = timed(e2e_step)
 
+    dec = None
+    if not args.no_decode:
+        dec_t, dec_n = decode_bench(model, pk, rank, world)
+        t = torch.tensor([dec_t["forced"], dec_t["natural"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dec = {"metric": "decode_utts_per_sec", "unit": "utts/s", "n_utts": 1000, "beam": 10, "max_token_seq_len": 100,
+               "value_forced_100_steps": 1000.0 / float(t[0]), "value_natural_eos": 1000.0 / float(t[1]),
+               "dtype": "f32", "sharding": "%d utterances per rank, no collective" % dec_n,
+               "timing": "wall clock around translate_batch over the rank's shard incl. H2D of features and D2H of lattices, max over ranks"}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -331,9 +414,18 @@ def run_b200(args):
         "clocks": clocks,
         "real_frames_per_step_per_gpu": float(np.mean(frames_pool)),
     }
+    if dec is not None:
+        line["decode"] = dec
     if world == 1:
+        if dec is not None:
+            try:
+                v = cpu_decode_baseline(4, 10, 100, os.cpu_count() or 1)
+                dec["cpu_baseline"] = {"value": v, "unit": "utts/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                       "sample": "4 utterances, beam 10, 100 forced steps, oracle port of L/decode.py:22-107 (no KV cache)"}
+            except Exception as exc:
+                dec["cpu_baseline"] = {"error": str(exc)[:200]}
         try:
-            line["roofline"] = roofline_probe(model, B, int(b0[1].shape[1]), pk)
+            line["roofline"] = roofline_probe(model, B, int(b0[1].shape[1]), pk, args.mode)
             line["roofline_hbm"] = hbm_probe()
         except Exception as exc:                                   # never lose the headline line to a probe
             line["roofline"] = {"error": str(exc)[:200]}
@@ -356,8 +448,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

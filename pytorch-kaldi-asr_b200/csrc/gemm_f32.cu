@@ -58,74 +58,110 @@ gemm_f32_kernel(const GemmParams p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int seg = 0; seg < p.nseg; ++seg) {
+  // ---- tile loaders: every thread first issues ALL its global loads of a tile into registers (compile-time trip
+  // counts -> the loads are in flight together), the registers are stored to shared memory after the previous tile's
+  // math, and the next tile's loads are issued before the math of the current one (register double buffering).
+  constexpr int RA = TA ? (BK / NW) * (BM / 32) : BM / NW;
+  constexpr int RB = TB ? BN / NW : (BK / NW) * (BN / 32);
+  float ra[RA], rb[RB];
+  const int k_iters = (k_end - k_begin + BK - 1) / BK;
+  const int n_it = k_end > k_begin ? p.nseg * k_iters : 0;
+
+  auto load_tile = [&](int it) {
+    const int seg = it / k_iters, k0 = k_begin + (it % k_iters) * BK;
     const float* __restrict__ As_g = Ab + (long long)seg * p.a_seg_off;
     const float* __restrict__ Bs_g = Bb + (long long)seg * p.b_seg_off;
-    const int shA = p.shiftA[seg < PKA_MAX_CTX ? seg : 0];
-    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-      // ---- A tile -> As[k][m]
-      if (!TA) {                      // A[M,K] row-major: lanes along k
-        const int k = k0 + lane;
-        for (int r = wrow; r < BM; r += NW) {
-          const int m = m_blk + r;
-          float v = 0.f;
-          if (m < p.M && k < k_end) {
-            bool ok = true;
-            if (p.T > 0) { int t = m % p.T + shA; ok = (t >= 0) && (t < p.T); }
-            if (ok) v = As_g[(long long)(m + shA) * p.lda + k];
-          }
-          As[lane][r] = v;
-        }
-      } else {                        // A stored [K,M]: lanes along m
-        for (int kk = wrow; kk < BK; kk += NW) {
-          const int k = k0 + kk;
+    if (!TA) {                        // A[M,K] row-major: lanes along k
+      const int shA = p.shiftA[seg < PKA_MAX_CTX ? seg : 0];
+      const int k = k0 + lane;
 #pragma unroll
-          for (int c = lane; c < BM; c += 32) {
-            const int m = m_blk + c;
-            As[kk][c] = (k < k_end && m < p.M) ? As_g[(long long)k * p.lda + m] : 0.f;
-          }
+      for (int i = 0; i < RA; ++i) {
+        const int m = m_blk + wrow + i * NW;
+        float v = 0.f;
+        if (m < p.M && k < k_end) {
+          bool ok = true;
+          if (p.T > 0) { int t = m % p.T + shA; ok = (t >= 0) && (t < p.T); }
+          if (ok) v = As_g[(long long)(m + shA) * p.lda + k];
+        }
+        ra[i] = v;
+      }
+    } else {                          // A stored [K,M]: lanes along m
+#pragma unroll
+      for (int i = 0; i < BK / NW; ++i) {
+        const int k = k0 + wrow + i * NW;
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) {
+          const int m = m_blk + lane + 32 * c;
+          ra[i * (BM / 32) + c] = (k < k_end && m < p.M) ? As_g[(long long)k * p.lda + m] : 0.f;
         }
       }
-      // ---- B tile -> Bs[k][n]
-      if (TB) {                       // B stored [N,K] (nn.Linear weight): lanes along k
-        const int k = k0 + lane;
-        for (int r = wrow; r < BN; r += NW) {
-          const int n = n_blk + r;
-          Bs[lane][r] = (n < p.N && k < k_end) ? Bs_g[(long long)n * p.ldb + k] : 0.f;
-        }
-      } else {                        // B stored [K,N]: lanes along n; optional frame shift on the reduction index
-        for (int kk = wrow; kk < BK; kk += NW) {
-          const int k = k0 + kk;
-          bool ok = k < k_end;
-          if (ok && p.T > 0) { int t = k % p.T + shiftB; ok = (t >= 0) && (t < p.T); }
-#pragma unroll
-          for (int c = lane; c < BN; c += 32) {
-            const int n = n_blk + c;
-            Bs[kk][c] = (ok && n < p.N) ? Bs_g[(long long)(k + shiftB) * p.ldb + n] : 0.f;
-          }
-        }
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int kk = 0; kk < BK; ++kk) {
-        float a[TM], b[TN];
-#pragma unroll
-        for (int g = 0; g < GM; ++g) {
-          float4 v = *reinterpret_cast<const float4*>(&As[kk][g * (BM / GM) + ty * 4]);
-          a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
-        }
-#pragma unroll
-        for (int g = 0; g < GN; ++g) {
-          float4 v = *reinterpret_cast<const float4*>(&Bs[kk][g * (BN / GN) + tx * 4]);
-          b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
-        }
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
     }
+    if (TB) {                         // B stored [N,K] (nn.Linear weight): lanes along k
+      const int k = k0 + lane;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int n = n_blk + wrow + i * NW;
+        rb[i] = (n < p.N && k < k_end) ? Bs_g[(long long)n * p.ldb + k] : 0.f;
+      }
+    } else {                          // B stored [K,N]: lanes along n; optional frame shift on the reduction index
+#pragma unroll
+      for (int i = 0; i < BK / NW; ++i) {
+        const int k = k0 + wrow + i * NW;
+        bool ok = k < k_end;
+        if (ok && p.T > 0) { int t = k % p.T + shiftB; ok = (t >= 0) && (t < p.T); }
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n = n_blk + lane + 32 * c;
+          rb[i * (BN / 32) + c] = (ok && n < p.N) ? Bs_g[(long long)(k + shiftB) * p.ldb + n] : 0.f;
+        }
+      }
+    }
+  };
+  auto store_tile = [&]() {
+    if (!TA) {
+#pragma unroll
+      for (int i = 0; i < RA; ++i) As[lane][wrow + i * NW] = ra[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < BK / NW; ++i)
+#pragma unroll
+        for (int c = 0; c < BM / 32; ++c) As[wrow + i * NW][lane + 32 * c] = ra[i * (BM / 32) + c];
+    }
+    if (TB) {
+#pragma unroll
+      for (int i = 0; i < RB; ++i) Bs[lane][wrow + i * NW] = rb[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < BK / NW; ++i)
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) Bs[wrow + i * NW][lane + 32 * c] = rb[i * (BN / 32) + c];
+    }
+  };
+
+  if (n_it > 0) load_tile(0);
+  for (int it = 0; it < n_it; ++it) {
+    store_tile();
+    __syncthreads();
+    if (it + 1 < n_it) load_tile(it + 1);
+#pragma unroll 8
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][g * (BM / GM) + ty * 4]);
+        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][g * (BN / GN) + tx * 4]);
+        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
   }
 
   if (p.splitk > 1) {              // raw partial sums; splitk_reduce_kernel finishes in a fixed order

@@ -83,10 +83,10 @@ def gemm(A, B, Cout, M, N, K, *, nseg=1, nbatch=1, lda, ldb, ldc, transA=False, 
     d.drop = _cdrop(drop)
     ws = None
     plain = bias is None and not relu and residual is None and (drop is None or not drop.on)
-    if transA and nseg == 1 and plain and K >= 1024:
+    if transA and nseg == 1 and plain and K >= 256:
         # weight gradients reduce over all frames but have few output tiles: split K so the grid fills the 148 SMs
         tiles = ((M + 63) // 64) * ((N + 63) // 64) * nbatch
-        splitk = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+        splitk = max(1, min((K + 63) // 64, (2 * 148 + tiles - 1) // tiles))
         if splitk > 1:
             ws = torch.empty(splitk * nbatch * M * N, device=A.device, dtype=torch.float32)
             d.splitk = splitk
