@@ -233,12 +233,13 @@ def decode_bench(model, pk, rank, world, n_total=1000, batch=125, beam=10, max_l
     pk.set_compute_mode("fp32")
     feats, _ = synthetic.utterances(n_total, np.random.RandomState(4321))
     lo, hi = parallel.shard_range(n_total, rank, world)
-    mine = feats[lo:hi]
-    mine.sort(key=lambda f: len(f))                               # length-sorted batches waste less padding
+    src_all, mask_all = pad_to_longest(feats[lo:hi])              # one padded length per shard -> one step graph
     batches = []
-    for i in range(0, len(mine), batch):
-        src, mask = pad_to_longest(mine[i:i + batch])
-        batches.append((None, torch.from_numpy(src).pin_memory(), torch.from_numpy(mask).pin_memory(), None, None))
+    for i in range(0, hi - lo, batch):
+        if i + batch > hi - lo:
+            i = max(0, hi - lo - batch)                           # last batch re-decodes a few utterances, same shape
+        batches.append((None, torch.from_numpy(src_all[i:i + batch]).pin_memory(),
+                        torch.from_numpy(mask_all[i:i + batch]).pin_memory(), None, None))
     out = {}
     for forced in (True, False):
         opt = types.SimpleNamespace(use_gpu=True, beam_size=beam, max_token_seq_len=max_len, nbest=1, force_full_length=forced)

@@ -1,5 +1,5 @@
 // bf16 tensor-core GEMM family for sm_100a: tcgen05.mma (UMMA 128x128x16, cta_group::1) with fp32 accumulators in
-// TMEM, operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring, warp-specialised:
+// TMEM, operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a 3-stage mbarrier ring (two CTAs per SM), warp-specialised:
 //   warp 0    TMA producer (one elected lane)
 //   warp 1    MMA issuer   (one elected lane; tcgen05.commit releases smem stages / publishes the accumulator)
 //   warp 2    TMEM allocator
@@ -18,12 +18,13 @@
 //                    frames is split over `splits` CTAs per tile (fp32 partials, summed in fixed order afterwards).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace pka {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;   // 3 x 32 KB stages -> two CTAs per SM
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2, TC_B_BYTES = TC_BN * TC_BK * 2;
-constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 constexpr int TC_THREADS = 192;
 
 struct TcParams {
@@ -37,6 +38,7 @@ struct TcParams {
   int relu;
   int M;                       // mode 1: rows of dZt (output channels)
   int utt_per_split, tb_per_utt;
+  int dbg;                     // diagnostics (env PKA_TC_DBG): 1 = skip the MMAs, 2 = skip the TMA loads
   pka_dropout drop;
 };
 
@@ -102,7 +104,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_
 constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);       // A and B MN-major (mode 2)
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -150,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int s = i % TC_STAGES, round = i / TC_STAGES;
         mbar_wait(smem_u32(&bars[TC_STAGES + s]), (round & 1) ^ 1);
         const uint32_t full = smem_u32(&bars[s]);
+        if (p.dbg & 2) { mbar_expect_tx(full, 0); continue; }
         mbar_expect_tx(full, TC_A_BYTES + TC_B_BYTES);
         if (p.mode == 0) {
           const int seg = i / p.kb_per_seg, kb = i % p.kb_per_seg;
@@ -175,7 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int s = i % TC_STAGES, round = i / TC_STAGES;
         mbar_wait(smem_u32(&bars[s]), round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (p.mode != 2) {
+        if (p.dbg & 1) {
+          if (i == 0) umma_f16(tmem_base, make_sdesc(smem_u32(sA)), make_sdesc(smem_u32(sB)), kIdesc, 0u);
+        } else if (p.mode != 2) {
           const uint64_t da = make_sdesc(smem_u32(sA + s * TC_A_BYTES));
           const uint64_t db = make_sdesc(smem_u32(sB + s * TC_B_BYTES));
 #pragma unroll
@@ -195,13 +200,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {                                         // ===== epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // row of the 128-row tile held by this thread
+    // stage the bias of this CTA's 128 columns in shared memory while the main loop runs
+    float* sbias = reinterpret_cast<float*>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 256);   // 16-byte aligned
+    {
+      const int e = threadIdx.x - 64;              // 0..127
+      const int n = n0 + e;
+      sbias[e] = (p.mode == 0 && p.bias && n < p.N) ? p.bias[n] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     if (num_k_iters > 0) {
       mbar_wait(smem_u32(&bars[2 * TC_STAGES]), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    DropCtx dc = make_drop(p.drop);
+    const DropCtx dc = make_drop(p.drop);
+    const float relu_floor = p.relu ? 0.f : -3.4e38f;
+    const bool skip_all = (p.dbg & 8) != 0;
 #pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
+    for (int c = 0; c < (skip_all ? 0 : TC_BN / 32); ++c) {
       uint32_t r[32];
       if (num_k_iters > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       else {
@@ -209,20 +224,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       const int nb = n0 + c * 32;
+      if (nb >= p.N) break;                        // warp-uniform: nothing left in this tile
+      const bool full = nb + 32 <= p.N;
+      float v[32];
       if (p.mode == 0) {
         const int t = t0 + row;
-        const bool valid = t < p.T;
+        const bool valid = t < p.T && !(p.dbg & 4);
         const long long m = (long long)b0 * p.T + t;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          const int n = nb + j;
-          if (p.bias && n < p.N) x += p.bias[n];
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = x;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(&sbias[c * 32 + j]);
+          v[j] = fmaxf(__uint_as_float(r[j]) + bv.x, relu_floor);
+          v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + bv.y, relu_floor);
+          v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + bv.z, relu_floor);
+          v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + bv.w, relu_floor);
         }
-        if (dc.p > 0.f && valid) {
+        if (dc.p > 0.f) {                          // N % 4 == 0 is required with dropout, so groups of 4 never straddle N
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (nb + j < p.N) {
@@ -234,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (valid) {
           if (p.c_dtype == PKA_BF16) {
             __nv_bfloat16* dst = (__nv_bfloat16*)p.C + m * p.ldc + nb;
-            if (nb + 32 <= p.N && (p.ldc & 7) == 0) {
+            if (full && (p.ldc & 7) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 pk;
@@ -249,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           } else {
             float* dst = (float*)p.C + m * p.ldc + nb;
-            if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+            if (full && (p.ldc & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
@@ -264,12 +281,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 32; ++j) if (nb + j < p.N) dt[(long long)(nb + j) * pitch] = __float2bfloat16_rn(v[j]);
           }
         }
-      } else {                                     // mode 1: fp32 partial of dW rows (output channels)
+      } else {                                     // modes 1/2: fp32 partial of dW rows (output channels)
         const int o = t0 + row;
         if (o < p.M) {
           float* dst = (float*)p.C + ((long long)blockIdx.z * p.M + o) * p.ldc + (long long)seg_fixed * p.N + nb;
+          if (full && (p.ldc & 3) == 0 && (p.N & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __uint_as_float(r[j]);
+          }
         }
       }
     }
@@ -427,6 +451,7 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
   p.kb_per_seg = (d->K + TC_BK - 1) / TC_BK;
   p.tiles_per_utt = (d->T + TC_BM - 1) / TC_BM;
   p.utt_per_split = 0; p.tb_per_utt = 0;
+  { const char* e = getenv("PKA_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap mapA, mapB;
   dim3 grid;
   int rc;
