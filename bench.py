@@ -391,9 +391,7 @@ def run_b200(args):
                "dtype": "f32", "sharding": "%d utterances per rank, no collective" % dec_n,
                "timing": "wall clock around translate_batch over the rank's shard incl. H2D of features and D2H of lattices, max over ranks"}
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _finish(world)
         return
     value = frames_res / (ms_res * 1e-3)
     e2e_value = frames_e2e / (ms_e2e * 1e-3)
@@ -437,9 +435,19 @@ def run_b200(args):
                                 "sample": "8 steps x 32 utterances (same synthetic batches), oracle port of the reference "
                                           "train step, dropout 0.35, %.0f s of CPU work" % (time.time() - t0)}
     print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroying a process group whose collectives were captured into CUDA graphs can
+    block forever at exit, so after a last barrier every rank flushes and exits hard."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
+        import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
