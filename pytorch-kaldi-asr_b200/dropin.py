@@ -1,0 +1,36 @@
+"""Make the reference's own import lines resolve to this package.
+
+The reference scripts (L/train.py, L/decode.py, L/initialize_model.py) import their model code through PYTHONPATH
+(P/path.sh:7-13) as top-level modules:
+
+    from transformer.Models import Transformer          from transformer.Optim import ScheduledOptim
+    from transformer.Lattice import Lattice             from TDNN import TDNNLayer, ConcatLayer, LDALayer
+    from utils import constants, instances_handler
+
+`import pytorch_kaldi_asr_b200.dropin` (before those lines) registers the B200 implementations under exactly these
+names, so the scripts run unchanged apart from that one import.  `utils.BatchLoader` / `kaldi_io` (Kaldi file I/O) are
+NOT provided -- they are outside the hot path and keep coming from the reference tree.
+"""
+import sys
+
+from . import TDNN as _tdnn
+from . import transformer as _transformer
+from . import utils as _utils
+from .transformer import Lattice as _lattice, Layers as _layers, Models as _models, Modules as _modules
+from .transformer import Optim as _optim, SubLayers as _sublayers
+from .utils import constants as _constants, instances_handler as _ih
+
+
+def install(override_utils: bool = False):
+    sys.modules["transformer"] = _transformer
+    for name, mod in (("Models", _models), ("Modules", _modules), ("SubLayers", _sublayers), ("Layers", _layers),
+                      ("Optim", _optim), ("Lattice", _lattice)):
+        sys.modules["transformer." + name] = mod
+    sys.modules["TDNN"] = _tdnn
+    if override_utils or "utils" not in sys.modules:
+        sys.modules.setdefault("utils", _utils)
+        sys.modules.setdefault("utils.constants", _constants)
+        sys.modules.setdefault("utils.instances_handler", _ih)
+
+
+install()
