@@ -151,6 +151,13 @@ int pka_attn_bwd(const pka_attn_desc* d, int dtype, const void* q, const void* k
                  const uint8_t* key_mask, const void* out, const void* dout, const float* lse, float* delta_ws,
                  void* dq, void* dk, void* dv, void* stream);
 
+/* Tensor-core forward of the same op for bf16 q/k/v with dk = dv = 64 (tcgen05.mma S = Q K^T and O = P V with fp32
+ * accumulators in TMEM, Q/K/V tiles staged by TMA, online softmax between the two MMAs; the mask stays a predicate).
+ * out: bf16 or f32 [B,Lq,ldo] (out_dtype); lse as above.  The matching backward is pka_attn_bwd on the same buffers
+ * (dtype PKA_BF16) -- both regenerate identical dropout bits. */
+int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void* k, const void* v, const uint8_t* key_mask,
+                    void* out, int out_dtype, float* lse, void* stream);
+
 /* ---- (c) fused [dropout] + residual add + LayerNormalization ----------------------------------------------------
  * replaces: `layer_norm(dropout(x) + residual)` (T/SubLayers.py:65-68,85-86) with LayerNormalization of
  * T/Modules.py:42-51: y = (z-mean)/(std_unbiased+eps)*a + b.  The "identity when size(1)==1" rule is applied by the

@@ -16,8 +16,7 @@
 // mode 1 ("wgrad"):  dW[o, seg*Ki+i] = sum_{b,t} dZt[o,b,t] * Xt[i,b,t+shift[seg]]       weight-gradient
 //                    both operands are the transposed activations (frames contiguous = K-major), reduction over all
 //                    frames is split over `splits` CTAs per tile (fp32 partials, summed in fixed order afterwards).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace pka {
@@ -42,66 +41,9 @@ struct TcParams {
   pka_dropout drop;
 };
 
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor: K-major tile of [rows][64 bf16] written by TMA with 128B swizzle (8-row atoms of 1 KB)
-// (lbo_bytes = 16, unused) -- or an MN-major tile made of [64 k-rows][64 bf16] TMA boxes: 8 k-rows x 128 B atoms,
-// SBO = 1024 B between 8-row k groups, LBO = byte distance between consecutive 64-element MN blocks.
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes = 16) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address            bits [0,14)
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;         // leading byte offset
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);       // A and B MN-major (mode 2)
+// instruction descriptors: D=F32, A=B=BF16, N=128, M=128; both K-major (modes 0/1) or both MN-major (mode 2)
+constexpr uint32_t kIdesc = make_idesc(TC_BM, TC_BN);
+constexpr uint32_t kIdescMN = make_idesc(TC_BM, TC_BN, true, true);
 
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -385,10 +327,7 @@ __global__ void relu_bwd_dual_kernel(const Tin* __restrict__ dY, const __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -400,7 +339,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D bf16 tensor map, innermost dim first; box = {64, box1, box2}; 128B swizzle; OOB elements read as zero
-static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                     uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who) {
   // cuTensorMapEncodeTiled is a driver call and needs a current context in THIS thread.  Autograd worker threads may
   // not have one bound yet when their first call into the library is a tensor-core GEMM, so make the (statically
@@ -418,7 +357,7 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, 
               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, box1, box2};
+  cuuint32_t box[3] = {64u, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

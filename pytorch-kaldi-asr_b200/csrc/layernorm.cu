@@ -154,10 +154,15 @@ __global__ void ln_dab_finish_kernel(const float* __restrict__ ws, float* __rest
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * D) return;
   const int which = e / D, col = e % D;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += ws[((long long)b * 2 + which) * D + col];
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  int b = 0;
+  for (; b + 4 <= nblk; b += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] += ws[((long long)(b + u) * 2 + which) * D + col];
+  }
+  for (; b < nblk; ++b) s[0] += ws[((long long)b * 2 + which) * D + col];
   float* dst = which == 0 ? da : db;
-  dst[col] += s;
+  dst[col] += (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 template <typename T>
@@ -191,7 +196,8 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
 
 extern "C" int pka_ln_bwd_blocks(int rows) {
   int need = (rows + pka::kLnWarps - 1) / pka::kLnWarps;
-  int cap = pka::kNumSMs * 2;
+  // few partial rows keep the fixed-order finish short (small decoder tensors); one CTA per SM for large ones
+  int cap = rows <= 8192 ? 64 : pka::kNumSMs;
   return need < cap ? (need > 0 ? need : 1) : cap;
 }
 

@@ -375,10 +375,74 @@ class _AttnFn(torch.autograd.Function):
         return dqbuf, dkvbuf, None, None, None, None, None, None, None
 
 
+class _AttnTcFn(torch.autograd.Function):
+    """bf16 attention on the tensor cores (pka_attn_tc_fwd: tcgen05 S = Q K^T / O = P V, TMA-fed, online softmax).
+    Same packed-buffer convention as _AttnFn; q/k/v and the output are bf16, statistics fp32."""
+
+    @staticmethod
+    def forward(ctx, qbuf, kvbuf, key_mask, H, dk, band, scale, drop, out_fp32):
+        L.require_cuda(qbuf, kvbuf, key_mask)
+        assert qbuf.dtype == torch.bfloat16 and (kvbuf is None or kvbuf.dtype == torch.bfloat16)
+        qbuf = qbuf.contiguous()
+        HD = H * dk
+        B, Lq = qbuf.shape[0], qbuf.shape[1]
+        if kvbuf is None:
+            Lk, ldq = Lq, 3 * HD
+            q_p, k_p, v_p, ldk = qbuf.data_ptr(), qbuf.data_ptr() + 2 * HD, qbuf.data_ptr() + 4 * HD, 3 * HD
+        else:
+            kvbuf = kvbuf.contiguous()
+            Lk, ldq, ldk = kvbuf.shape[1], HD, 2 * HD
+            q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 2 * HD
+        key_mask = key_mask.to(torch.uint8).contiguous()
+        assert key_mask.shape == (B, Lk)
+        d = L.AttnDesc()
+        d.B, d.H, d.Lq, d.Lk, d.dk, d.dv = B, H, Lq, Lk, dk, dk
+        d.ldq, d.ldk, d.ldv, d.ldo = ldq, ldk, ldk, HD
+        d.use_band = int(band is not None)
+        d.band_start, d.band_end = (int(band[0]), int(band[1])) if band is not None else (0, 0)
+        d.scale = float(scale)
+        d.drop = _cdrop(drop)
+        out = torch.empty(B, Lq, HD, device=qbuf.device, dtype=torch.bfloat16)
+        lse = torch.empty(B, H, Lq, device=qbuf.device, dtype=torch.float32)
+        L.check(L.lib().pka_attn_tc_fwd(C.byref(d), C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p), L.ptr(key_mask),
+                                        L.ptr(out), L.PKA_BF16, L.ptr(lse), L.stream_ptr()), "attn_tc_fwd")
+        ctx.save_for_backward(qbuf, kvbuf, key_mask, out, lse)
+        ctx.desc = d
+        ctx.mark_non_differentiable(lse)
+        return (out.float() if out_fp32 else out), lse
+
+    @staticmethod
+    def backward(ctx, dout, _dlse):
+        qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
+        d = ctx.desc
+        HD = d.H * d.dk
+        dout = dout.to(torch.bfloat16).contiguous()
+        dqbuf = torch.empty_like(qbuf)
+        if kvbuf is None:
+            dkvbuf = None
+            q_p, k_p, v_p = qbuf.data_ptr(), qbuf.data_ptr() + 2 * HD, qbuf.data_ptr() + 4 * HD
+            dq_p, dk_p, dv_p = dqbuf.data_ptr(), dqbuf.data_ptr() + 2 * HD, dqbuf.data_ptr() + 4 * HD
+        else:
+            dkvbuf = torch.empty_like(kvbuf)
+            q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 2 * HD
+            dq_p, dk_p, dv_p = dqbuf.data_ptr(), dkvbuf.data_ptr(), dkvbuf.data_ptr() + 2 * HD
+        delta = torch.empty_like(lse)
+        L.check(L.lib().pka_attn_bwd(C.byref(d), L.PKA_BF16, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
+                                     L.ptr(key_mask), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta),
+                                     C.c_void_p(dq_p), C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_bwd")
+        return dqbuf, dkvbuf, None, None, None, None, None, None, None
+
+
 def attention(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, drop: Optional[Drop] = None,
               want_probs: bool = False):
     out, _lse, probs = _AttnFn.apply(qbuf, kvbuf, key_mask, n_head, d_k, band, scale, drop, want_probs)
     return out, probs
+
+
+def attention_tc(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, drop: Optional[Drop] = None,
+                 out_fp32: bool = False):
+    """bf16 packed projections -> bf16 (or fp32) context on the tcgen05 attention kernel; returns (out, lse)."""
+    return _AttnTcFn.apply(qbuf, kvbuf, key_mask, n_head, d_k, band, scale, drop, out_fp32)
 
 
 # ------------------------------------------------------------------------------------------------ add + LayerNorm
