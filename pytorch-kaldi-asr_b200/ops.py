@@ -243,7 +243,8 @@ class _HeadProjFn(torch.autograd.Function):
 
     @staticmethod
     def _forward_tc(ctx, x, ws):
-        """bf16 x [Bt,T,D] (the encoder memory for cross-attention K/V): one tcgen05 GEMM for all P*H heads, fp32 out."""
+        """bf16 x [Bt,T,D]: one tcgen05 GEMM for all P*H heads; the packed q|k|v (or k|v) buffer stays bf16 because its
+        only consumer is the tensor-core attention kernel."""
         assert x.dim() == 3 and x.is_contiguous()
         Bt, T, D = x.shape
         H, _, dk = ws[0].shape
@@ -255,7 +256,7 @@ class _HeadProjFn(torch.autograd.Function):
         wp = [L.ptr(w.detach()) for w in ws] + [C.c_void_p(0)] * (3 - P)
         L.check(L.lib().pka_head_weight_relayout(wp[0], wp[1], wp[2], P, H, D, dk, L.ptr(wf), L.ptr(wd), L.stream_ptr()),
                 "head_weight_relayout")
-        out = gemm_tc_rows(x, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.float32)
+        out = gemm_tc_rows(x, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.bfloat16)
         ctx.tc = True
         ctx.save_for_backward(x, wd)
         ctx.meta = (Bt, T, D, H, dk, P)
@@ -266,7 +267,7 @@ class _HeadProjFn(torch.autograd.Function):
         x, wd = ctx.saved_tensors
         Bt, T, D, H, dk, P = ctx.meta
         ntot = P * H * dk
-        dz = gate_to_bf16(dy, Bt, T, ntot)
+        dz = dy if (dy.dtype == torch.bfloat16 and dy.is_contiguous()) else gate_to_bf16(dy, Bt, T, ntot)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot)
@@ -402,21 +403,22 @@ class _AttnTcFn(torch.autograd.Function):
         d.band_start, d.band_end = (int(band[0]), int(band[1])) if band is not None else (0, 0)
         d.scale = float(scale)
         d.drop = _cdrop(drop)
-        out = torch.empty(B, Lq, HD, device=qbuf.device, dtype=torch.bfloat16)
+        out = torch.empty(B, Lq, HD, device=qbuf.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
         lse = torch.empty(B, H, Lq, device=qbuf.device, dtype=torch.float32)
         L.check(L.lib().pka_attn_tc_fwd(C.byref(d), C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p), L.ptr(key_mask),
-                                        L.ptr(out), L.PKA_BF16, L.ptr(lse), L.stream_ptr()), "attn_tc_fwd")
+                                        L.ptr(out), L.dtype_code(out), L.ptr(lse), L.stream_ptr()), "attn_tc_fwd")
         ctx.save_for_backward(qbuf, kvbuf, key_mask, out, lse)
         ctx.desc = d
         ctx.mark_non_differentiable(lse)
-        return (out.float() if out_fp32 else out), lse
+        return out, lse
 
     @staticmethod
     def backward(ctx, dout, _dlse):
         qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
         d = ctx.desc
         HD = d.H * d.dk
-        dout = dout.to(torch.bfloat16).contiguous()
+        dout = cast(dout, torch.bfloat16).contiguous()
+        out = cast(out, torch.bfloat16)
         dqbuf = torch.empty_like(qbuf)
         if kvbuf is None:
             dkvbuf = None
@@ -494,14 +496,14 @@ def add_layer_norm(x, residual, a, b, eps: float = 1e-3, drop: Optional[Drop] = 
 # ------------------------------------------------------------------------------------------------ embedding, positions
 class _EmbedPosFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tok, emb, pos, drop, padding_idx):
+    def forward(ctx, tok, emb, pos, drop, padding_idx, out_dtype):
         L.require_cuda(tok, emb, pos)
         tok = tok.to(torch.int64).contiguous()
         B, Ln = tok.shape
         V, D = emb.shape
         assert pos.shape[0] >= Ln, "sequence length %d exceeds the position table (%d)" % (Ln, pos.shape[0])
-        out = torch.empty(B, Ln, D, device=emb.device, dtype=torch.float32)
-        L.check(L.lib().pka_embed_pos_fwd(L.ptr(tok), L.ptr(emb), L.ptr(pos), L.ptr(out), L.PKA_F32, B, Ln, D, V,
+        out = torch.empty(B, Ln, D, device=emb.device, dtype=out_dtype)
+        L.check(L.lib().pka_embed_pos_fwd(L.ptr(tok), L.ptr(emb), L.ptr(pos), L.ptr(out), L.dtype_code(out), B, Ln, D, V,
                                           _byref_drop(drop), L.stream_ptr()), "embed_pos_fwd")
         ctx.save_for_backward(tok)
         ctx.meta = (V, D, drop, padding_idx)
@@ -514,13 +516,39 @@ class _EmbedPosFn(torch.autograd.Function):
         B, Ln = tok.shape
         dout = dout.contiguous()
         demb = torch.zeros(V, D, device=dout.device, dtype=torch.float32)
-        L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.PKA_F32, B, Ln, D, V, padding_idx,
+        L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.dtype_code(dout), B, Ln, D, V, padding_idx,
                                       _byref_drop(drop), L.stream_ptr()), "embed_bwd")
-        return None, demb, None, None, None
+        return None, demb, None, None, None, None
 
 
-def embed_pos(tok, emb, pos, drop: Optional[Drop] = None, padding_idx: int = 0):
-    return _EmbedPosFn.apply(tok, emb, pos, drop, padding_idx)
+def embed_pos(tok, emb, pos, drop: Optional[Drop] = None, padding_idx: int = 0, out_dtype=torch.float32):
+    return _EmbedPosFn.apply(tok, emb, pos, drop, padding_idx, out_dtype)
+
+
+class _CastFn(torch.autograd.Function):
+    """dtype conversion between the bf16 activation stream and fp32 consumers (pka_cast); the gradient is cast back."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        L.require_cuda(x)
+        x = x.contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=dtype)
+        L.check(L.lib().pka_cast(L.ptr(x), L.dtype_code(x), L.ptr(out), L.dtype_code(out), C.c_int64(x.numel()), L.stream_ptr()),
+                "cast")
+        ctx.src_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty(dy.shape, device=dy.device, dtype=ctx.src_dtype)
+        L.check(L.lib().pka_cast(L.ptr(dy), L.dtype_code(dy), L.ptr(dx), L.dtype_code(dx), C.c_int64(dy.numel()), L.stream_ptr()),
+                "cast")
+        return dx, None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else _CastFn.apply(x, dtype)
 
 
 class _AddRowvecDropoutFn(torch.autograd.Function):

@@ -84,6 +84,8 @@ class Encoder(nn.Module):
 
     def forward(self, src_seq, src_pad_mask, return_attns=False):
         dev = src_seq.device
+        if ops.compute_mode() == "bf16":       # bf16 activation stream: the front-end kernel makes the bf16 copy
+            src_seq = ops.frontend(src_seq, None, 1, [0], 0, out_dtype=torch.bfloat16)
         x = self.src_projection(src_seq)
         x = ops.add_pos_dropout(x, self.position_enc.weight, self._rng.make(self.p, self._site_in, dev, self.training))
         mask = get_attn_padding_mask(src_pad_mask, src_pad_mask) + get_attn_subsequent_mask(src_pad_mask, *self.sub)
@@ -158,9 +160,13 @@ class Decoder(nn.Module):
         dev = enc_output.device
         # bf16 mode: the projected encoder memory stays bf16 -- its only consumers are the cross-attention K/V
         # projections (the largest decoder GEMMs: all T frames, every layer), which then run on the tensor cores too
-        enc = self.enc_dec_projection(enc_output, out_fp32=(ops.compute_mode() != "bf16"))
+        bf16 = ops.compute_mode() == "bf16" and tgt_seq.size(1) > 1
+        if bf16 and enc_output.dtype != torch.bfloat16:
+            enc_output = ops.cast(enc_output, torch.bfloat16)
+        enc = self.enc_dec_projection(enc_output, out_fp32=not bf16)
         x = ops.embed_pos(tgt_seq, self.tgt_word_emb.weight, self.position_enc.weight,
-                          self._rng.make(self.p, self._site_emb, dev, self.training), constants.PAD)
+                          self._rng.make(self.p, self._site_emb, dev, self.training), constants.PAD,
+                          out_dtype=torch.bfloat16 if bf16 else torch.float32)
         slf_mask = get_attn_padding_mask(tgt_pad_mask, tgt_pad_mask) + get_attn_subsequent_mask(tgt_pad_mask, *self.sub)
         enc_mask = get_attn_padding_mask(tgt_pad_mask, src_pad_mask)
         slf_attns, enc_attns = [], []
@@ -170,7 +176,9 @@ class Decoder(nn.Module):
             slf_attns.append(a1)
             enc_attns.append(a2)
         x = ops.add_pos_dropout(x, None, self._rng.make(self.p, self._site_out, dev, self.training))
-        logits = self.tgt_word_proj(x)
+        # V = 53 columns do not meet TMA's 16-byte row pitch for the data-gradient operand: the vocabulary projection
+        # (0.3 % of the step's FLOPs) stays on the fp32 GEMM and hands fp32 logits to the loss
+        logits = self.tgt_word_proj(ops.cast(x, torch.float32))
         return (logits, slf_attns, enc_attns) if return_attns else (logits,)
 
 

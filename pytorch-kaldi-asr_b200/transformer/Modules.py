@@ -89,4 +89,8 @@ class ScaledDotProductAttention(nn.Module):
 
     def forward(self, qbuf, kvbuf, mask: AttnMask, n_head, d_k, want_probs=False):
         drop = self._rng.make(self.p, self._site, qbuf.device, self.training)
+        if qbuf.dtype == torch.bfloat16:
+            assert not want_probs, "the attention maps are only materialised on the fp32 path"
+            ctx, _lse = ops.attention_tc(qbuf, kvbuf, mask.key_pad_mask, n_head, d_k, mask.band, 1.0 / self.temper, drop)
+            return ctx, None
         return ops.attention(qbuf, kvbuf, mask.key_pad_mask, n_head, d_k, mask.band, 1.0 / self.temper, drop, want_probs)

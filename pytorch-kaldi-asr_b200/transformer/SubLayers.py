@@ -45,6 +45,9 @@ class MultiHeadAttention(nn.Module):
             qbuf, kvbuf = ops.head_proj(q, self.w_qs), ops.head_proj(k, self.w_ks, self.w_vs)
         ctx, probs = self.attention(qbuf, kvbuf, attn_mask, self.n_head, self.d_k, want_probs=self.return_attn)
         drop = self._rng.make(self.p, self._site, q.device, self.training)
+        if q.dtype == torch.bfloat16:  # bf16 activation stream: tensor-core projections / attention, bf16 LayerNorm I/O
+            assert q.size(1) > 1, "the bf16 path is the training path; single-token decoding runs in fp32"
+            return self.layer_norm(self.proj(ctx), residual=q, drop=drop), probs
         if q.size(1) == 1:          # LayerNormalization is the identity for length-1 inputs (T/Modules.py:43-44)
             out = self.proj(ctx, drop=drop, residual=q)
         else:
@@ -69,6 +72,10 @@ class PositionwiseFeedForward(nn.Module):
 
     def forward(self, x):
         drop = self._rng.make(self.p, self._site, x.device, self.training)
+        if x.dtype == torch.bfloat16:  # both GEMMs on tcgen05 with fused bias(+ReLU) epilogues
+            h = ops.linear_tc(x, self.w_1.weight, self.w_1.bias, relu=True)
+            y = ops.linear_tc(h, self.w_2.weight, self.w_2.bias)
+            return self.layer_norm(y, residual=x, drop=drop)
         h = ops.linear(x, self.w_1.weight, self.w_1.bias, relu=True)
         if x.size(1) == 1:
             return ops.linear(h, self.w_2.weight, self.w_2.bias, drop=drop, residual=x)
