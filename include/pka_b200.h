@@ -158,6 +158,14 @@ int pka_attn_bwd(const pka_attn_desc* d, int dtype, const void* q, const void* k
 int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void* k, const void* v, const uint8_t* key_mask,
                     void* out, int out_dtype, float* lse, void* stream);
 
+/* Tensor-core backward for the same bf16 buffers (q/k/v/out/dout and dq/dk/dv all bf16, leading dimensions as in `d`):
+ * two launches of one kernel template -- dQ over query tiles, then dK/dV over key tiles -- each recomputing
+ * S = Q K^T and dP = dO V^T with tcgen05.mma, forming dS = P (M dP - delta) in registers and accumulating
+ * dQ = dS K / dK = dS^T Q / dV = (P M)^T dO in TMEM.  No atomics: bit-reproducible.  delta_ws: float[B*H*Lq]. */
+int pka_attn_tc_bwd(const pka_attn_desc* d, const void* q, const void* k, const void* v, const uint8_t* key_mask,
+                    const void* out, const void* dout, const float* lse, float* delta_ws, void* dq, void* dk, void* dv,
+                    void* stream);
+
 /* ---- (c) fused [dropout] + residual add + LayerNormalization ----------------------------------------------------
  * replaces: `layer_norm(dropout(x) + residual)` (T/SubLayers.py:65-68,85-86) with LayerNormalization of
  * T/Modules.py:42-51: y = (z-mean)/(std_unbiased+eps)*a + b.  The "identity when size(1)==1" rule is applied by the

@@ -429,10 +429,18 @@ class _AttnTcFn(torch.autograd.Function):
             q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 2 * HD
             dq_p, dk_p, dv_p = dqbuf.data_ptr(), dkvbuf.data_ptr(), dkvbuf.data_ptr() + 2 * HD
         delta = torch.empty_like(lse)
-        L.check(L.lib().pka_attn_bwd(C.byref(d), L.PKA_BF16, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
-                                     L.ptr(key_mask), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta),
-                                     C.c_void_p(dq_p), C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_bwd")
+        if ATTN_BWD_TC:
+            L.check(L.lib().pka_attn_tc_bwd(C.byref(d), C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p), L.ptr(key_mask),
+                                            L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta), C.c_void_p(dq_p),
+                                            C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_tc_bwd")
+        else:
+            L.check(L.lib().pka_attn_bwd(C.byref(d), L.PKA_BF16, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
+                                         L.ptr(key_mask), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta),
+                                         C.c_void_p(dq_p), C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_bwd")
         return dqbuf, dkvbuf, None, None, None, None, None, None, None
+
+
+ATTN_BWD_TC = True      # False: the SIMT flash backward on the same bf16 buffers (kept for A/B comparison in the tests)
 
 
 def attention(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, drop: Optional[Drop] = None,
@@ -632,6 +640,13 @@ def dropout_keep_mask(n: int, drop: Drop, device) -> torch.Tensor:
     keep = torch.empty(n, device=device, dtype=torch.uint8)
     L.check(L.lib().pka_dropout_mask(L.ptr(keep), C.c_int64(n), C.byref(drop.c()), L.stream_ptr()), "dropout_mask")
     return keep
+
+
+def attn_keep_mask(B: int, H: int, Lq: int, Lk: int, drop: Drop, device) -> torch.Tensor:
+    """Keep bits [B,H,Lq,Lk] of an attention-probability dropout site: the kernels index element (b,h,i,j) as
+    ((b*H+h)*Lq+i)*Lk4 + j with Lk4 = Lk rounded up to a multiple of 4 -- for parity tests only."""
+    Lk4 = (Lk + 3) // 4 * 4
+    return dropout_keep_mask(B * H * Lq * Lk4, drop, device).view(B, H, Lq, Lk4)[..., :Lk].contiguous()
 
 
 # ================================================================================================ bf16 tensor-core path

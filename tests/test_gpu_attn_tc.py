@@ -96,7 +96,7 @@ def test_attn_tc_dropout_uses_the_shared_philox_bits():
     step = torch.full((1,), 7, dtype=torch.int64, device=DEV)
     drop = ops.Drop(0.35, 11, 1234, step)
     out, _ = ops.attention_tc(qb.to(DEV), kv.to(DEV), key_mask.to(DEV), H, D, None, scale, drop, True)
-    keep = ops.dropout_keep_mask(B * H * Lq * Lk, drop, DEV).view(B, H, Lq, Lk).float().cpu()
+    keep = ops.attn_keep_mask(B, H, Lq, Lk, drop, DEV).float().cpu()
     split = lambda t, L_: t.float().view(B, L_, H, D).permute(0, 2, 1, 3)
     ref, _ = ref_attention(split(qb, Lq), split(kv[..., :HD], Lk), split(kv[..., HD:], Lk), key_mask, None, scale,
                            keep=keep, drop_scale=1.0 / 0.65)
@@ -105,24 +105,62 @@ def test_attn_tc_dropout_uses_the_shared_philox_bits():
     assert float((got - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
 
 
-def test_attn_tc_backward_matches_autograd_of_the_oracle():
-    """Gradients of the bf16 path (tensor-core forward + its backward kernels) against autograd through the fp32 checker."""
+BWD_CASES = [
+    # B, H, Lq, Lk, band, pad, self, dropout
+    (2, 2, 63, 300, None, 50, False, 0.0),        # TIMIT-like cross-attention
+    (2, 2, 63, 63, (-10, 0), 7, True, 0.0),       # decoder self-attention band
+    (2, 4, 300, 300, (-100, 0), 33, True, 0.0),   # banded encoder self-attention, several tiles both ways
+    (1, 2, 200, 333, None, 0, False, 0.35),       # dropout: backward regenerates the forward's Philox bits
+    (1, 2, 150, 150, (-20, 5), 10, True, 0.35),
+    (1, 1, 128, 128, (5, 9), 0, True, 0.0),       # rows without any allowed key: zero gradient
+]
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,band,pad,self_attn,pdrop", BWD_CASES)
+@pytest.mark.parametrize("tc_bwd", [True, False])
+def test_attn_tc_backward_matches_autograd_of_the_oracle(B, H, Lq, Lk, band, pad, self_attn, pdrop, tc_bwd):
+    """Gradients of the bf16 path (tensor-core forward + tensor-core / SIMT backward kernels) against autograd through
+    the fp32 checker on the same bf16-rounded inputs.  Stated tolerance: 2e-2 of each gradient tensor's scale."""
     from pytorch_kaldi_asr_b200 import ops
-    B, H, Lq, Lk, D = 2, 2, 63, 300, 64
-    HD = H * D
+    D, HD = 64, H * 64
     scale = 1.0 / math.sqrt(128.0)
-    qb = rnd(B, Lq, HD, seed=5).bfloat16()
-    kv = rnd(B, Lk, 2 * HD, seed=6).bfloat16()
-    gy = rnd(B, Lq, HD, seed=7).bfloat16()
     key_mask = torch.ones(B, Lk, dtype=torch.uint8)
-    key_mask[0, 250:] = 0
-    qg, kvg = qb.to(DEV).requires_grad_(True), kv.to(DEV).requires_grad_(True)
-    out, _ = ops.attention_tc(qg, kvg, key_mask.to(DEV), H, D, None, scale, None, False)
-    out.backward(gy.to(DEV))
-    qr, kvr = qb.float().requires_grad_(True), kv.float().requires_grad_(True)
+    for b in range(B):
+        n_pad = (pad * (b + 1)) // B if pad else 0
+        if n_pad:
+            key_mask[b, Lk - n_pad:] = 0
+    gy = rnd(B, Lq, HD, seed=7).bfloat16()
+    drop, keep = None, None
+    if pdrop > 0:
+        drop = ops.Drop(pdrop, 5, 4321, torch.full((1,), 3, dtype=torch.int64, device=DEV))
+        keep = ops.attn_keep_mask(B, H, Lq, Lk, drop, DEV).float().cpu()
     split = lambda t, L_: t.view(B, L_, H, D).permute(0, 2, 1, 3)
-    ref, _ = ref_attention(split(qr, Lq), split(kvr[..., :HD], Lk), split(kvr[..., HD:], Lk), key_mask, None, scale)
+    old = ops.ATTN_BWD_TC
+    ops.ATTN_BWD_TC = tc_bwd
+    try:
+        if self_attn:
+            qkv = rnd(B, Lq, 3 * HD, seed=5).bfloat16()
+            xg = qkv.to(DEV).requires_grad_(True)
+            out, _ = ops.attention_tc(xg, None, key_mask.to(DEV), H, D, band, scale, drop, False)
+            out.backward(gy.to(DEV))
+            xr = qkv.float().requires_grad_(True)
+            ref, _ = ref_attention(split(xr[..., :HD], Lq), split(xr[..., HD:2 * HD], Lk), split(xr[..., 2 * HD:], Lk), key_mask,
+                                   band, scale, keep=keep, drop_scale=1.0 / (1.0 - pdrop))
+            pairs = [(xg, xr)]
+        else:
+            qb = rnd(B, Lq, HD, seed=5).bfloat16()
+            kv = rnd(B, Lk, 2 * HD, seed=6).bfloat16()
+            qg, kvg = qb.to(DEV).requires_grad_(True), kv.to(DEV).requires_grad_(True)
+            out, _ = ops.attention_tc(qg, kvg, key_mask.to(DEV), H, D, band, scale, drop, False)
+            out.backward(gy.to(DEV))
+            qr, kvr = qb.float().requires_grad_(True), kv.float().requires_grad_(True)
+            ref, _ = ref_attention(split(qr, Lq), split(kvr[..., :HD], Lk), split(kvr[..., HD:], Lk), key_mask, band, scale,
+                                   keep=keep, drop_scale=1.0 / (1.0 - pdrop))
+            pairs = [(qg, qr), (kvg, kvr)]
+    finally:
+        ops.ATTN_BWD_TC = old
     ref.permute(0, 2, 1, 3).reshape(B, Lq, HD).backward(gy.float())
-    for got, want in ((qg.grad, qr.grad), (kvg.grad, kvr.grad)):
-        g, w = got.float().cpu(), want
-        assert float((g - w).abs().max()) <= 2e-2 * float(w.abs().max())
+    for got, want in pairs:
+        g, w = got.grad.float().cpu(), want.grad
+        assert torch.isfinite(g).all()
+        assert float((g - w).abs().max()) <= 2e-2 * float(w.abs().max()), (float((g - w).abs().max()), float(w.abs().max()))

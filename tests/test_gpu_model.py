@@ -181,7 +181,10 @@ def test_train_mode_dropout_parity_with_injected_masks():
     masks = {}
     for name, shp in shapes.items():
         d = ops.Drop(0.35, sites[name], model.dropout_state.seed, step)
-        masks[name] = ops.dropout_keep_mask(int(np.prod(shp)), d, DEV).cpu().view(shp)
+        if name.endswith(".attn"):
+            masks[name] = ops.attn_keep_mask(*shp, d, DEV).cpu()
+        else:
+            masks[name] = ops.dropout_keep_mask(int(np.prod(shp)), d, DEV).cpu().view(shp)
     plan = am.DropoutPlan("injected", masks)
     logits_ref, loss_ref, _, _, grads_ref = otrain.loss_and_grads(sd, cfg, batch[1:], False, plan)
     assert sorted(set(plan.visited)) == sorted(shapes)

@@ -173,7 +173,7 @@ def test_attention_fwd_bwd(B, H, Lq, Lk, D, band, selfattn, p):
     keep, drop = None, None
     if p > 0:
         drop = o.Drop(p, 5, 99, torch.tensor([3], dtype=torch.int64, device=DEV))
-        keep = o.dropout_keep_mask(B * H * Lq * Lk, drop, DEV).cpu().view(B, H, Lq, Lk).float()
+        keep = o.attn_keep_mask(B, H, Lq, Lk, drop, DEV).cpu().float()
     qr = qbuf.clone().requires_grad_(True)
     kvr = kvbuf.clone().requires_grad_(True) if kvbuf is not None else None
     if selfattn:
