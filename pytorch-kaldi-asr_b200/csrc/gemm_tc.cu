@@ -369,12 +369,21 @@ int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_
 
 }  // namespace pka
 
+namespace pka { int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled); }   // gemm_tc_rows.cu
+
 using namespace pka;
 
 extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
   PKA_REQUIRE(d && d->A && d->B && d->C, PKA_EINVAL, "gemm_tc: null operand");
   PKA_REQUIRE(d->Bt > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->nseg >= 1 && d->nseg <= PKA_MAX_CTX, PKA_EINVAL,
               "gemm_tc: bad sizes Bt=%d T=%d N=%d K=%d nseg=%d", d->Bt, d->T, d->N, d->K, d->nseg);
+  if (d->mode == 0) {                              // A-stationary / B-multicast kernel whenever the problem fits it
+    PKA_REQUIRE(d->nseg == 1 || d->K % TC_BK == 0, PKA_EUNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d when nseg>1", d->K, TC_BK);
+    PKA_REQUIRE(d->drop.p == 0.f || d->N % 4 == 0, PKA_EUNSUPPORTED, "gemm_tc: dropout epilogue needs N%%4==0");
+    bool handled = false;
+    int rc2 = launch_rows2(d, as_stream(stream), &handled);
+    if (rc2 || handled) return rc2;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
