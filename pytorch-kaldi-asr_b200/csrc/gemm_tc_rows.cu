@@ -8,8 +8,10 @@
 // by L2 bandwidth at a third of the tensor peak.  Here:
 //   * A (activations): one CTA owns a 128-frame tile for ALL output columns and keeps it resident in shared memory,
 //     loaded ONCE with an 8-frame halo on each side (TMA zero-fills beyond the utterance = ConcatLayer's padding).  The
-//     frame shift of a splice context is a row offset of the UMMA descriptor start address inside the 128B-swizzled
-//     tile (matrix base offset = row & 7), so the n_ctx shifted views cost no traffic at all.
+//     frame shift of a splice context is a row offset (128 B per frame) of the UMMA descriptor start address inside the
+//     128B-swizzled tile, so the n_ctx shifted views cost no traffic at all.  (Measured on B200: the swizzle XOR is
+//     taken from the absolute shared-memory address bits, so a start address that is not 1 KB aligned needs NO
+//     "matrix base offset" in the descriptor -- setting it to (addr >> 7) & 7 gives wrong products.)
 //   * B (weights): streamed in [128 x 64] stages through a deep mbarrier ring; the CTAs of a thread-block cluster
 //     (different frame tiles, same weights) each fetch 1/CL of every stage and TMA-multicast it to all of them.
 //   * accumulators: one 128-column TMEM buffer per 128-column output tile (up to 4); the epilogue of tile n
@@ -20,9 +22,11 @@
 namespace pka {
 
 constexpr int R2_BM = 128, R2_BN = 128, R2_BK = 64, R2_HALO = 8;
-constexpr int R2_B_BYTES = R2_BN * R2_BK * 2;               // 16 KB per stage
-constexpr int R2_MAX_STAGES = 8, R2_MAX_NT = 4, R2_MAX_KB = 8;
-constexpr int R2_THREADS = 192;
+constexpr int R2_BOX_BYTES = R2_BN * R2_BK * 2;             // one [128 x 64] weight box = 16 KB
+constexpr int R2_STAGE_BYTES = 2 * R2_BOX_BYTES;            // a stage holds two consecutive K blocks (K = 128)
+constexpr int R2_C_BYTES = R2_BM * 64 * 2;                  // output staging tile [128 rows][64 bf16] for the TMA store
+constexpr int R2_MAX_STAGES = 6, R2_MAX_NT = 4, R2_MAX_KB = 8;
+constexpr int R2_THREADS = 352;                             // warp 0 / warp 10 TMA (even / odd stages), warp 1 MMA, warps 2-9 epilogue
 
 struct Rows2Params {
   int Bt, T, N, K, nseg;
@@ -30,8 +34,10 @@ struct Rows2Params {
   int b_seg_col;
   int shift[PKA_MAX_CTX];
   int halo, a_rows, a_blk_bytes;                 // rows per resident A block (128 + 2*halo), bytes per 64-column block
-  int stages, nt;                                // B ring depth, number of 128-column output tiles
-  int use_base_offset;
+  int stages, nt;                                // B ring depth, number of output-column chunks (one TMEM accumulator each)
+  int chunk, stage_bytes;                        // columns per chunk (128; pair mode: up to 256), bytes of one B stage per CTA
+  int use_base_offset, dbg;                      // diagnostics (env PKA_TC_BASEOFF / PKA_TC_DBG: 1 skip MMAs, 4 skip stores, 8 skip epilogue, 16 stamps)
+  int tma_store;                                 // bf16 output through shared memory + cp.async.bulk.tensor stores
   void* C; int ldc, c_dtype;
   const float* bias; int relu;
   pka_dropout drop;
@@ -39,6 +45,10 @@ struct Rows2Params {
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_relaxed() {     // execution barrier only (no memory fence: no MEMBAR.ALL.GPU)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -51,15 +61,51 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// CTA-pair (cta_group::2) variants: the load signals the LEADER CTA's mbarrier (peer bit cleared), the MMA spans both
+// SMs (M = 256: each CTA's tensor core works on its own 128 rows, B rows are split between the two shared memories)
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// diagnostics (PKA_TC_DBG & 16): per-CTA globaltimer stamps, read back with pka_debug_rows2_stamps()
+__device__ unsigned long long g_rows2_ts[256 * 16];
+__device__ __forceinline__ void stamp(int dbg, int slot) {
+  if (dbg & 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x < 256 && blockIdx.y == 0) g_rows2_ts[blockIdx.x * 16 + slot] = t;
+  }
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(R2_THREADS, 1)
-gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Rows2Params p) {
+gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapC, const Rows2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int a_bytes = p.kb_per_seg * p.a_blk_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + a_bytes;
-  uint64_t* bars = (uint64_t*)(sB + p.stages * R2_B_BYTES);
-  // bars: [0,8) a_full per K block, [8,16) b_full, [16,24) b_empty, [24,28) acc_full per output tile; then TMEM slot, bias
+  uint8_t* sC = sB + p.stages * p.stage_bytes;
+  uint64_t* bars = (uint64_t*)(sC + 2 * R2_C_BYTES);
+  // bars: [0,8) a_full per K block, [8,14) b_full, [14,20) b_empty, [20,24) acc_full per output tile; then TMEM slot, bias
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + R2_MAX_KB;
   uint64_t* b_empty = b_full + R2_MAX_STAGES;
@@ -71,150 +117,284 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) stamp(p.dbg, 0);
 
   const bool tile_ok = (int)blockIdx.x < p.n_tiles_m;
   const int b0 = tile_ok ? blockIdx.x / p.tiles_per_utt : p.Bt;                 // padded CTAs read (zero-filled) utterance Bt
   const int t0 = tile_ok ? (blockIdx.x % p.tiles_per_utt) * R2_BM : 0;
-  const int nbase = blockIdx.y * (R2_MAX_NT * R2_BN);
-  const int n_k = p.nseg * p.kb_per_seg;           // B stages per output tile
-  const int total = p.nt * n_k;
+  const int nbase = blockIdx.y * (p.nt * p.chunk);
+  const int box_bytes = p.stage_bytes >> 1;
+  const bool leader = !PAIR || rank == 0;
+  const int kp_per_seg = (p.kb_per_seg + 1) >> 1;  // stages per splice context (two K blocks each, the last may hold one)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < R2_MAX_KB; ++i) mbar_init(smem_u32(&a_full[i]), 1);
-    for (int s = 0; s < R2_MAX_STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), csize); }
+    for (int s = 0; s < R2_MAX_STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), PAIR ? 1u : csize); }
     for (int i = 0; i < R2_MAX_NT; ++i) mbar_init(smem_u32(&acc_full[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc<512>(smem_u32(tmem_slot));
-  tc_fence_before();
-  __syncthreads();
-  if (csize > 1) cluster_sync_all();               // every CTA's barriers exist before any remote arrive / multicast
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {                               // ===== TMA producer
-      tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
-      for (int kb = 0; kb < p.kb_per_seg; ++kb) {  // resident activations: [a_rows][64] per K block, halo rows included
-        mbar_expect_tx(smem_u32(&a_full[kb]), (uint32_t)p.a_blk_bytes);
-        tma_load_3d(smem_u32(sA + kb * p.a_blk_bytes), &mapA, smem_u32(&a_full[kb]), kb * R2_BK, t0 - p.halo, b0);
-      }
-      const int rows_per_cta = R2_BN / (int)csize;
-      for (int i = 0; i < total; ++i) {
-        const int s = i % p.stages, round = i / p.stages;
-        mbar_wait(smem_u32(&b_empty[s]), (round & 1) ^ 1);      // all CTAs of the cluster have released this stage
-        const uint32_t full = smem_u32(&b_full[s]);
-        mbar_expect_tx(full, R2_B_BYTES);
-        const int nt = i / n_k, kk = i % n_k;
-        const int seg = kk / p.kb_per_seg, kb = kk % p.kb_per_seg;
-        const int col = seg * p.b_seg_col + kb * R2_BK;
-        const int row = nbase + nt * R2_BN + (int)rank * rows_per_cta;
-        const uint32_t dst = smem_u32(sB + s * R2_B_BYTES + (int)rank * rows_per_cta * 128);
-        if (csize > 1) tma_load_3d_mc(dst, &mapB, full, col, row, 0, cmask);
-        else tma_load_3d(dst, &mapB, full, col, row, 0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {                               // ===== MMA issuer
-      const uint32_t idesc = make_idesc(R2_BM, R2_BN);
-      for (int i = 0; i < total; ++i) {
-        const int s = i % p.stages, round = i / p.stages;
-        const int nt = i / n_k, kk = i % n_k;
-        const int seg = kk / p.kb_per_seg, kb = kk % p.kb_per_seg;
-        if (nt == 0 && seg == 0) mbar_wait(smem_u32(&a_full[kb]), 0);
-        mbar_wait(smem_u32(&b_full[s]), round & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + kb * p.a_blk_bytes) + (uint32_t)(p.halo + p.shift[seg]) * 128u;
-        uint64_t da = make_sdesc(a_addr);
-        if (p.use_base_offset) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-        const uint64_t db = make_sdesc(smem_u32(sB + s * R2_B_BYTES));
-#pragma unroll
-        for (int k = 0; k < R2_BK / 16; ++k)
-          umma_f16(tmem_base + (uint32_t)(nt * R2_BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kk | k) ? 1u : 0u);
-        if (csize > 1) umma_commit_mc(smem_u32(&b_empty[s]), cmask);
-        else umma_commit(smem_u32(&b_empty[s]));
-        if (kk == n_k - 1) umma_commit(smem_u32(&acc_full[nt]));
-      }
-    }
-  } else {                                         // ===== epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    for (int e = threadIdx.x - 64; e < p.nt * R2_BN; e += 128) {
-      const int n = nbase + e;
-      sbias[e] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const DropCtx dc = make_drop(p.drop);
-    const float relu_floor = p.relu ? 0.f : -3.4e38f;
-    const int t = t0 + row;
-    const bool valid = tile_ok && t < p.T;
-    const long long m = (long long)b0 * p.T + t;
-    for (int nt = 0; nt < p.nt; ++nt) {
-      mbar_wait(smem_u32(&acc_full[nt]), 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < R2_BN / 32; ++c) {
-        const int nb = nbase + nt * R2_BN + c * 32;
-        if (nb >= p.N) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(nt * R2_BN + c * 32), r);
-        const bool full = nb + 32 <= p.N;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(&sbias[nt * R2_BN + c * 32 + j]);
-          v[j] = fmaxf(__uint_as_float(r[j]) + bv.x, relu_floor);
-          v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + bv.y, relu_floor);
-          v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + bv.z, relu_floor);
-          v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + bv.w, relu_floor);
-        }
-        if (dc.p > 0.f) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j < p.N) {
-              const float4 mul = dropout_mul4(dc, ((unsigned long long)m * p.N + nb + j) >> 2);
-              v[j] *= mul.x; v[j + 1] *= mul.y; v[j + 2] *= mul.z; v[j + 3] *= mul.w;
-            }
-          }
-        }
-        if (valid) {
-          if (p.c_dtype == PKA_BF16) {
-            __nv_bfloat16* dst = (__nv_bfloat16*)p.C + m * p.ldc + nb;
-            if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                *reinterpret_cast<uint4*>(dst + j) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else {
-            float* dst = (float*)p.C + m * p.ldc + nb;
-            if (full && (p.ldc & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
-            }
-          }
-        }
-      }
+  if (warp == 2) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc<512>(smem_u32(tmem_slot));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();               // nobody leaves while a peer may still multicast into / arrive on its smem
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (csize > 1) cluster_sync_relaxed();           // every CTA's barriers exist (fence.mbarrier_init above) before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(p.dbg, 1);
+
+  if (warp == 0 || warp == 10) {
+    const int pid = warp == 0 ? 0 : 1;             // two producer threads on different schedulers: even / odd stages
+    if (lane == 0) {                               // ===== TMA producer (no divisions in the loop: it paces the whole CTA)
+      tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      const int rows_per_cta = PAIR ? (p.chunk >> 1) : R2_BN / (int)csize;
+      const uint32_t slice_off = PAIR ? 0u : rank * (uint32_t)rows_per_cta * 128u;
+      int a_next = 0;
+      auto issue_a = [&]() {                       // resident activations: [a_rows][64] per K block, halo rows included
+        const uint32_t bar = smem_u32(&a_full[a_next]);
+        if (PAIR) {                                // both CTAs' tiles complete on the leader's barrier
+          if (leader) mbar_expect_tx(bar, 2u * (uint32_t)p.a_blk_bytes);
+          tma_load_3d_pair(sA_u + a_next * p.a_blk_bytes, &mapA, bar, a_next * R2_BK, t0 - p.halo, b0);
+        } else {
+          mbar_expect_tx(bar, (uint32_t)p.a_blk_bytes);
+          tma_load_3d(sA_u + a_next * p.a_blk_bytes, &mapA, bar, a_next * R2_BK, t0 - p.halo, b0);
+        }
+        ++a_next;
+      };
+      if (pid == 0) {
+        issue_a();
+        if (p.kb_per_seg > 1) issue_a();
+      } else {
+        a_next = p.kb_per_seg;                     // the activations are producer 0's job
+      }
+      int s = 0, istage = 0;
+      uint32_t ph = 0;
+      for (int nt = 0; nt < p.nt; ++nt) {
+        const int row = nbase + nt * p.chunk + (int)rank * rows_per_cta;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          int col = seg * p.b_seg_col, kb_left = p.kb_per_seg;
+          for (int kp = 0; kp < kp_per_seg; ++kp, col += 2 * R2_BK, kb_left -= 2, ++istage) {
+            if ((istage & 1) != pid) { if (++s == p.stages) { s = 0; ph ^= 1u; } continue; }
+            mbar_wait(smem_u32(&b_empty[s]), ph ^ 1u);          // every consumer of this stage has released it
+            const uint32_t full = smem_u32(&b_full[s]);
+            const uint32_t dst = sB_u + (uint32_t)s * p.stage_bytes + slice_off;
+            const int nbx = kb_left >= 2 ? 2 : 1;
+            if (PAIR) {
+              if (leader) mbar_expect_tx(full, 2u * (uint32_t)(nbx * box_bytes));
+              tma_load_3d_pair(dst, &mapB, full, col, row, 0);
+              if (nbx == 2) tma_load_3d_pair(dst + box_bytes, &mapB, full, col + R2_BK, row, 0);
+            } else {
+              mbar_expect_tx(full, (uint32_t)(nbx * box_bytes));
+              if (csize > 1) {
+                tma_load_3d_mc(dst, &mapB, full, col, row, 0, cmask);
+                if (nbx == 2) tma_load_3d_mc(dst + box_bytes, &mapB, full, col + R2_BK, row, 0, cmask);
+              } else {
+                tma_load_3d(dst, &mapB, full, col, row, 0);
+                if (nbx == 2) tma_load_3d(dst + box_bytes, &mapB, full, col + R2_BK, row, 0);
+              }
+            }
+            if (a_next < p.kb_per_seg) issue_a();
+            if (a_next < p.kb_per_seg) issue_a();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+      if (pid == 0) stamp(p.dbg, 4);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {                     // ===== MMA issuer (pair mode: the leader CTA issues for both SMs)
+      const uint32_t idesc = PAIR ? make_idesc(2 * R2_BM, p.chunk) : make_idesc(R2_BM, R2_BN);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int nt = 0; nt < p.nt; ++nt) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)(nt * p.chunk);
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const uint32_t a_off = (uint32_t)(p.halo + p.shift[seg]) * 128u;
+          int kb = 0;
+          for (int kp = 0; kp < kp_per_seg; ++kp) {
+            const int nb = min(2, p.kb_per_seg - kb);
+            if (nt == 0 && seg == 0) {
+              for (int j = 0; j < nb; ++j) mbar_wait(smem_u32(&a_full[kb + j]), 0);
+              if (kp == 0) stamp(p.dbg, 5);
+            }
+            mbar_wait(smem_u32(&b_full[s]), ph);
+            if (nt == 0 && seg == 0 && kp == 0) stamp(p.dbg, 6);
+            tc_fence_after();
+            for (int j = 0; j < nb; ++j, ++kb) {
+              const uint32_t a_addr = sA_u + (uint32_t)(kb * p.a_blk_bytes) + a_off;
+              uint64_t da = make_sdesc(a_addr);
+              if (p.use_base_offset) da |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+              const uint64_t db = make_sdesc(sB_u + (uint32_t)s * p.stage_bytes + (uint32_t)(j * box_bytes));
+              if (!(p.dbg & 1)) {
+#pragma unroll
+                for (int k = 0; k < R2_BK / 16; ++k) {
+                  if (PAIR) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (seg | kp | j | k) ? 1u : 0u);
+                  else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (seg | kp | j | k) ? 1u : 0u);
+                }
+              }
+            }
+            if (PAIR) umma_commit_pair(smem_u32(&b_empty[s]));
+            else if (csize > 1) umma_commit_mc(smem_u32(&b_empty[s]), cmask);
+            else umma_commit(smem_u32(&b_empty[s]));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+        if (PAIR) umma_commit_pair(smem_u32(&acc_full[nt]));
+        else umma_commit(smem_u32(&acc_full[nt]));
+        stamp(p.dbg, 7 + (nt & 1));
+      }
+    }
+  } else {                                         // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column group = (warp-2)/4
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;               // group g owns the 64-column slices g, g+2, ... of every accumulator
+    const int gtid = (int)threadIdx.x - 64 - grp * 128;
+    const int row = q * 32 + lane;
+    for (int e = threadIdx.x - 64; e < p.nt * p.chunk; e += 256) {
+      const int n = nbase + e;
+      sbias[e] = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");
+    const DropCtx dc = make_drop(p.drop);
+    const float relu_floor = p.relu ? 0.f : -3.4e38f;
+    const int t = t0 + row;
+    const bool valid = tile_ok && t < p.T && !(p.dbg & 4);
+    const long long m = (long long)b0 * p.T + t;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* sCg = sC + grp * R2_C_BYTES;
+    uint8_t* crow = sCg + (row >> 3) * 1024 + (row & 7) * 128;
+    bool store_pending = false;
+    // Dropout keep bits depend only on (row, column), not on the accumulators: generate them NOW, while the MMAs run,
+    // so that the Philox rounds are off the exposed epilogue (1 bit per element, <= 256 columns per thread).
+    uint32_t keep[8];
+    if (dc.p > 0.f) {
+      int w = 0;
+      for (int nt = 0; nt < p.nt; ++nt)
+        for (int hf = grp; hf < (p.chunk >> 6); hf += 2) {
+          const int nb0 = nbase + nt * p.chunk + hf * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c, ++w) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int nb = nb0 + c * 32 + j;
+              if (nb < p.N) {
+                const uint4 rnd = Philox::run(dc.seed, dc.site, dc.step, ((unsigned long long)m * p.N + nb) >> 2);
+                bits |= (rnd.x >= dc.thresh ? 1u : 0u) << j | (rnd.y >= dc.thresh ? 2u : 0u) << j |
+                        (rnd.z >= dc.thresh ? 4u : 0u) << j | (rnd.w >= dc.thresh ? 8u : 0u) << j;
+              }
+            }
+#pragma unroll
+            for (int z = 0; z < 8; ++z) if (w == z) keep[z] = bits;
+          }
+        }
+    }
+    int kw = 0;
+    for (int nt = 0; nt < p.nt; ++nt) {
+      mbar_wait(smem_u32(&acc_full[nt]), 0);
+      if (threadIdx.x == 64) stamp(p.dbg, 10 + (nt & 1));
+      if (threadIdx.x == 64 && nt == p.nt - 1) stamp(p.dbg, 12);
+      tc_fence_after();
+      if (p.dbg & 8) continue;
+#pragma unroll 1
+      for (int hf = grp; hf < (p.chunk >> 6); hf += 2) { // 64 output columns at a time
+        const int nb0 = nbase + nt * p.chunk + hf * 64;
+        if (nb0 >= p.N) break;
+        if (p.tma_store) {
+          if (store_pending) {                     // the previous bulk store must have read the staging tile
+            if (gtid == 0) tma_store_wait_read();
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nb = nb0 + c * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_addr + (uint32_t)(nt * p.chunk + hf * 64 + c * 32), r);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(&sbias[nt * p.chunk + hf * 64 + c * 32 + j]);
+            v[j] = fmaxf(__uint_as_float(r[j]) + bv.x, relu_floor);
+            v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + bv.y, relu_floor);
+            v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + bv.z, relu_floor);
+            v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + bv.w, relu_floor);
+          }
+          if (dc.p > 0.f) {
+            uint32_t bits = keep[0];
+#pragma unroll
+            for (int z = 1; z < 8; ++z) if (kw == z) bits = keep[z];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * dc.scale : 0.f;
+          }
+          ++kw;
+          if (p.tma_store) {                       // bf16 row segment -> swizzled staging tile (conflict-free 16 B stores)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8], v[g * 8 + 1]), h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]), h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+              pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+              *reinterpret_cast<uint4*>(crow + (((c * 4 + g) ^ (row & 7)) << 4)) = pk;
+            }
+          } else if (valid && nb < p.N) {
+            const bool full = nb + 32 <= p.N;
+            if (p.c_dtype == PKA_BF16) {
+              __nv_bfloat16* dst = (__nv_bfloat16*)p.C + m * p.ldc + nb;
+              if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                  pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                  *reinterpret_cast<uint4*>(dst + j) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
+              }
+            } else {
+              float* dst = (float*)p.C + m * p.ldc + nb;
+              if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+              }
+            }
+          }
+        }
+        if (p.tma_store) {
+          fence_async_smem();
+          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (gtid == 0 && tile_ok && !(p.dbg & 4)) tma_store_3d(&mapC, smem_u32(sCg), nb0, t0, b0);   // rows >= T are clipped
+          store_pending = true;
+        }
+      }
+    }
+    if (p.tma_store && gtid == 0) tma_store_wait_read();
+    if (threadIdx.x == 64) stamp(p.dbg, 14);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) stamp(p.dbg, 15);
+  if (csize > 1) cluster_sync_relaxed();           // nobody leaves while a peer may still multicast into / arrive on its smem
+  if (warp == 2) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // Can this mode-0 problem run on the A-stationary kernel?  On success fills the launch geometry.
-struct Rows2Plan { int halo, a_rows, a_blk_bytes, stages, nt, smem, cluster, grid_x, grid_y; };
+struct Rows2Plan { int halo, a_rows, a_blk_bytes, stages, nt, chunk, stage_bytes, pair, smem, cluster, grid_x, grid_y; };
 static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
   if (d->mode != 0 || d->Ct) return false;
   if (d->nseg > 1 && d->a_seg_col != 0) return false;
@@ -230,22 +410,41 @@ static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
   pl->a_rows = R2_BM + 2 * halo;
   pl->a_blk_bytes = pl->a_rows * 128;
   const int a_bytes = kb * pl->a_blk_bytes;
-  const int budget = 225 * 1024 - a_bytes - 256 - 2048 - 64;
-  int stages = budget / R2_B_BYTES;
+  const int tiles_m = d->Bt * ((d->T + R2_BM - 1) / R2_BM);
+  // CTA-pair mode (cta_group::2, M = 256): each CTA stages only HALF of every weight tile, which halves the dominant
+  // shared-memory ingress.  Needs equal column chunks of <= 256 that are multiples of 64, all in one CTA's 512 TMEM columns.
+  int pair = 0, nt = 0, chunk = R2_BN;
+  if (tiles_m >= 2) {
+    // 128-column chunks when possible: the epilogue of chunk n overlaps the MMAs of chunk n+1
+    if (d->N % 256 == 0 && d->N <= 512) { pair = 1; nt = d->N / 256; chunk = 256; }        // largest TMA boxes (16 KB)
+    else if (d->N % 128 == 0 && d->N <= 512) { pair = 1; nt = d->N / 128; chunk = 128; }
+    else if (d->N <= 256 && d->N % 64 == 0) { pair = 1; nt = 1; chunk = d->N; }
+    if (const char* e = getenv("PKA_TC_CHUNK")) { const int c = atoi(e); if (pair && c >= 64 && c <= 256 && c % 64 == 0 && d->N % c == 0 && d->N <= 512) { chunk = c; nt = d->N / c; } }
+  }
+  if (const char* e = getenv("PKA_TC_PAIR")) pair = pair && atoi(e) != 0;
+  pl->pair = pair;
+  if (pair) {
+    pl->nt = nt; pl->chunk = chunk; pl->grid_y = 1;
+    pl->stage_bytes = chunk * 128;                                       // two boxes of [chunk/2 rows][64]
+  } else {
+    const int n_tiles_n = (d->N + R2_BN - 1) / R2_BN;
+    pl->nt = n_tiles_n < R2_MAX_NT ? n_tiles_n : R2_MAX_NT;
+    pl->chunk = R2_BN;
+    pl->grid_y = (n_tiles_n + R2_MAX_NT - 1) / R2_MAX_NT;
+    if (pl->grid_y > 1 && n_tiles_n % R2_MAX_NT != 0) return false;    // keep every grid row on the same tile count
+    pl->stage_bytes = R2_STAGE_BYTES;
+  }
+  const int budget = 225 * 1024 - a_bytes - 2 * R2_C_BYTES - 256 - 2048 - 64;
+  int stages = budget / pl->stage_bytes;
   if (stages > R2_MAX_STAGES) stages = R2_MAX_STAGES;
   if (stages < 2) return false;
-  const int n_tiles_n = (d->N + R2_BN - 1) / R2_BN;
-  pl->nt = n_tiles_n < R2_MAX_NT ? n_tiles_n : R2_MAX_NT;
-  pl->grid_y = (n_tiles_n + R2_MAX_NT - 1) / R2_MAX_NT;
-  if (pl->grid_y > 1 && n_tiles_n % R2_MAX_NT != 0) return false;      // keep every grid row on the same tile count
-  const int total = pl->nt * d->nseg * kb;
+  const int total = pl->nt * d->nseg * ((kb + 1) / 2);
   if (stages > total) stages = total;
   pl->stages = stages;
-  pl->smem = a_bytes + stages * R2_B_BYTES + 256 + 2048;
+  pl->smem = a_bytes + stages * pl->stage_bytes + 2 * R2_C_BYTES + 256 + 2048;
   if (pl->smem < 116 * 1024) pl->smem = 116 * 1024;                      // one CTA per SM: it owns all 512 TMEM columns
-  const int tiles_m = d->Bt * ((d->T + R2_BM - 1) / R2_BM);
-  int cl = tiles_m >= 64 ? 4 : (tiles_m >= 8 ? 2 : 1);
-  if (const char* e = getenv("PKA_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cl = v; }
+  int cl = pair ? 2 : (tiles_m >= 64 ? 4 : (tiles_m >= 8 ? 2 : 1));
+  if (!pair) if (const char* e = getenv("PKA_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cl = v; }
   pl->cluster = cl;
   pl->grid_x = (tiles_m + cl - 1) / cl * cl;
   return true;
@@ -258,7 +457,8 @@ int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled) {
   if (!plan_rows2(d, &pl)) return PKA_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_rows2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_rows2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_tc rows2: cannot opt in to shared memory: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -270,15 +470,24 @@ int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled) {
   p.b_seg_col = d->b_seg_col;
   for (int i = 0; i < PKA_MAX_CTX; ++i) p.shift[i] = d->shift[i];
   p.halo = pl.halo; p.a_rows = pl.a_rows; p.a_blk_bytes = pl.a_blk_bytes;
-  p.stages = pl.stages; p.nt = pl.nt;
-  { const char* e = getenv("PKA_TC_BASEOFF"); p.use_base_offset = e ? atoi(e) : 1; }
+  p.stages = pl.stages; p.nt = pl.nt; p.chunk = pl.chunk; p.stage_bytes = pl.stage_bytes;
+  { const char* e = getenv("PKA_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("PKA_TC_BASEOFF"); p.use_base_offset = e ? atoi(e) : 0; }     // diagnostics only, see header
   p.C = d->C; p.ldc = d->ldc; p.c_dtype = d->c_dtype; p.bias = d->bias; p.relu = d->relu; p.drop = d->drop;
-  CUtensorMap mapA, mapB;
+  p.tma_store = (d->c_dtype == PKA_BF16 && d->ldc % 8 == 0 && aligned16(d->C)) ? 1 : 0;
+  if (const char* e = getenv("PKA_TC_TMASTORE")) p.tma_store = p.tma_store && atoi(e) != 0;
+  CUtensorMap mapA, mapB, mapC;
   int rc = make_map(&mapA, d->A, (uint64_t)d->K, d->T, d->Bt, (uint64_t)d->lda * 2, (uint64_t)d->T * d->lda * 2, pl.a_rows, 1, "gemm_tc A (resident)");
   if (rc) return rc;
   const uint64_t b_cols = (uint64_t)d->b_seg_col * (d->nseg - 1) + d->K;
-  rc = make_map(&mapB, d->B, b_cols, d->N, 1, (uint64_t)d->ldb * 2, (uint64_t)d->N * d->ldb * 2, R2_BN / pl.cluster, 1, "gemm_tc B (multicast)");
+  rc = make_map(&mapB, d->B, b_cols, d->N, 1, (uint64_t)d->ldb * 2, (uint64_t)d->N * d->ldb * 2, pl.pair ? pl.chunk / 2 : R2_BN / pl.cluster, 1, "gemm_tc B");
   if (rc) return rc;
+  if (p.tma_store) {
+    rc = make_map(&mapC, d->C, (uint64_t)d->N, d->T, d->Bt, (uint64_t)d->ldc * 2, (uint64_t)d->T * d->ldc * 2, R2_BM, 1, "gemm_tc C (store)");
+    if (rc) return rc;
+  } else {
+    mapC = mapA;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid_x, pl.grid_y, 1);
   cfg.blockDim = dim3(R2_THREADS, 1, 1);
@@ -288,10 +497,15 @@ int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pl.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_rows2_kernel, mapA, mapB, p);
+  cudaError_t e = pl.pair ? cudaLaunchKernelEx(&cfg, gemm_tc_rows2_kernel<true>, mapA, mapB, mapC, p)
+                          : cudaLaunchKernelEx(&cfg, gemm_tc_rows2_kernel<false>, mapA, mapB, mapC, p);
   PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_tc rows2 launch failed: %s", cudaGetErrorString(e));
   *handled = true;
   return check_launch("gemm_tc rows2");
 }
 
 }  // namespace pka
+
+extern "C" int pka_debug_rows2_stamps(unsigned long long* host, int n_bytes) {
+  return cudaMemcpyFromSymbol(host, pka::g_rows2_ts, n_bytes) == cudaSuccess ? 0 : 4;
+}
