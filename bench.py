@@ -199,7 +199,8 @@ def roofline_probe(model, B, T, pk, mode):
 
         secs = {"fwd": time_kernel(fwd), "dgrad": time_kernel(dgrad), "wgrad": time_kernel(wgrad)}
         sec = secs["fwd"]
-        out["kernel"] = "gemm_tc_kernel (tcgen05.mma 128x128x16, TMEM accumulators, TMA 128B-swizzle, spliced TDNN forward)"
+        out["kernel"] = ("gemm_tc_rows2_kernel<pair> (tcgen05.mma cta_group::2 256x256x16, TMEM accumulators, activations resident "
+                         "with splice halo, split weight tiles by TMA, TMA-store epilogue; spliced TDNN forward)")
         out["family_us"] = {k: v * 1e6 for k, v in secs.items()}
         out["family_tflops"] = {k: flops / v / 1e12 for k, v in secs.items()}
     else:
@@ -236,6 +237,66 @@ def hbm_probe():
     gbs = 3.0 * rows * D * 4 / sec / 1e9
     return {"kernel": "add_ln_fwd_kernel", "achieved": gbs, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk_["hbm_gbs"],
             "bytes_per_launch": 3 * rows * D * 4}
+
+
+def cfg5_bench(B=4, band=(-100, 0), steps=5, warmup=3, profile=False):
+    """BASELINE config 5 (the attention stress case): self-attention `Encoder` 12 layers + `Decoder` 6 layers, d_model 512,
+    H=8, d_k=d_v=64, ~1500-frame utterances (T_i = clip(N(1500,100),1200,1599), L_i = T_i//10), bf16 tensor-core path,
+    one training step = forward + summed CE + backward + Adam, replayed as one CUDA graph."""
+    import pytorch_kaldi_asr_b200 as pk
+    from pytorch_kaldi_asr_b200.utils import synthetic
+    pk.set_compute_mode("bf16")
+    cfg = dict(n_src_dim=40, n_tgt_vocab=53, encoder_max_len=1600, decoder_max_len=200, src_fold=1,
+               encoder_sub_sequence=band, decoder_sub_sequence=(-20, 0), en_layers=12, de_layers=6, n_head=8,
+               en_d_model=512, de_d_model=512, d_k=64, d_v=64, en_dropout=0.1, de_dropout=0.1)
+    torch.manual_seed(0)
+    model = pk.Transformer(lda_mat=None, encoder_type="attention", **cfg).cuda()
+    opt = pk.ScheduledOptim(pk.FusedAdam(model.parameters(), betas=(0.9, 0.999), eps=1e-8), 1e-3, 25000)
+    pool = synthetic.batches(4, B, seed=555, pad_to="set", mean_len=1500.0, std_len=100.0, min_len=1200, max_len=1599,
+                             label_div=10, max_labels=198)
+    dev_pool = [pk.train._to_device(b, "cuda", non_blocking=False) for b in pool]
+    frames = [synthetic.real_frames(b) for b in pool]
+    model.train()
+    graphed = pk.GraphedTrainStep(model, opt, pool[0])        # all batches are padded to one shape -> one CUDA graph
+
+    def step(i):
+        graphed.load(*dev_pool[i % len(dev_pool)])
+        graphed.graph.replay()
+        return graphed.out[0]
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        loss = step(warmup + i)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    fr = float(np.mean([frames[(warmup + i) % len(frames)] for i in range(steps)]))
+    n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    out = {"workload": "cfg5: Encoder 12L + Decoder 6L, d_model 512, H=8, T~1500 (BASELINE configs[4])", "batch": B,
+           "band": list(band), "padded_T": int(pool[0][1].shape[1]), "padded_L": int(pool[0][3].shape[1] - 1),
+           "ms_per_step": ms, "frames_per_sec": fr / (ms * 1e-3), "utts_per_sec": B / (ms * 1e-3), "trainable_params": int(n_par),
+           "loss_finite": bool(torch.isfinite(loss).item()), "dtype": "bf16", "execution": "cuda-graph"}
+    if profile:
+        import collections, re
+        from torch.profiler import profile as tprofile, ProfilerActivity
+        with tprofile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(0)
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                name = re.sub(r"\(.*", "", ev.name)[:70]
+                agg[name][0] += 1
+                agg[name][1] += ev.device_time_total
+        tot = sum(v[1] for v in agg.values())
+        out["kernel_us_per_step"] = tot
+        out["top_kernels"] = [(k, round(v[1], 1), v[0]) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]]
+    pk.set_compute_mode("bf16")
+    return out
 
 
 def decode_bench(model, pk, rank, world, n_total=1000, batch=125, beam=10, max_len=100):
@@ -445,6 +506,13 @@ def run_b200(args):
             line["roofline_hbm"] = hbm_probe()
         except Exception as exc:                                   # never lose the headline line to a probe
             line["roofline"] = {"error": str(exc)[:200]}
+        if not args.no_cfg5:
+            try:
+                line["cfg5"] = cfg5_bench(B=8, band=(-100, 0), steps=5, warmup=3)
+                line["cfg5_full_attention"] = cfg5_bench(B=4, band=(-1600, 1600), steps=3, warmup=2)
+                pk.set_compute_mode(args.mode)
+            except Exception as exc:
+                line["cfg5"] = {"error": str(exc)[:200]}
         threads = os.cpu_count() or 1
         t0 = time.time()
         v, ms = cpu_train_baseline(32, 8, 1, threads)
@@ -477,6 +545,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

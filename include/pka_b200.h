@@ -173,7 +173,7 @@ int pka_attn_tc_bwd(const pka_attn_desc* d, const void* q, const void* k, const 
 int pka_add_layernorm_fwd(const void* x, const void* residual, const float* a, const float* b, void* y, float* mean,
                           float* rinv, int dtype, int rows, int D, float eps, const pka_dropout* drop, void* stream);
 /* dres always written; dx written only when drop->p > 0 (otherwise dx == dres and may be NULL).
- * dab_ws: float[2*D*pka_ln_bwd_blocks(rows)] scratch; da/db are *accumulated into* (+=). */
+ * dab_ws: float[2*D*pka_ln_bwd_blocks(rows)] scratch; da/db are overwritten. */
 int pka_ln_bwd_blocks(int rows);
 int pka_add_layernorm_bwd(const void* dy, const void* x, const void* residual, const float* a, const float* mean,
                           const float* rinv, void* dx, void* dres, float* da, float* db, float* dab_ws, int dtype,
@@ -193,7 +193,8 @@ int pka_ce_bwd(const void* logits, const int64_t* goal, const float* lse, const 
  * out[b,l,:] = dropout(emb[tok[b,l],:] + pos[l,:])           (T/Models.py:195-213) */
 int pka_embed_pos_fwd(const int64_t* tok, const float* emb, const float* pos, void* out, int dtype, int B, int L,
                       int D, int V, const pka_dropout* drop, void* stream);
-/* demb[v,:] += sum over (b,l) with tok==v of dropout_bwd(dout[b,l,:]); row `padding_idx` is left untouched.
+/* demb[v,:] = sum over (b,l) with tok==v of dropout_bwd(dout[b,l,:]); every row is written (row `padding_idx` and
+ * rows of unseen tokens get zeros), so the caller can pass the gradient slot itself without clearing it.
  * Deterministic (one CTA per vocabulary row, fixed summation order). */
 int pka_embed_bwd(const int64_t* tok, const void* dout, float* demb, int dtype, int B, int L, int D, int V,
                   int padding_idx, const pka_dropout* drop, void* stream);

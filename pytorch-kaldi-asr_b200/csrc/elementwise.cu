@@ -69,7 +69,10 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __r
   __shared__ int match[kEmbChunk];
   __shared__ int n_match;
   const int v = blockIdx.x;
-  if (v == padding_idx) return;
+  if (v == padding_idx) {                          // nn.Embedding(padding_idx): this row never receives a gradient
+    for (int c = threadIdx.x; c < D; c += blockDim.x) demb[(long long)v * D + c] = 0.f;
+    return;
+  }
   DropCtx dc = make_drop(drop);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long base = 0; base < n_tok; base += kEmbChunk) {
@@ -95,7 +98,8 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __r
         if (dc.p > 0.f) g = dropout_keep(dc, (unsigned long long)(r * D + c)) ? g * dc.scale : 0.f;
         acc += g;
       }
-      if (nm) demb[(long long)v * D + c] += acc;
+      if (base == 0) demb[(long long)v * D + c] = acc;          // the first chunk defines the row (no zero fill needed)
+      else if (nm) demb[(long long)v * D + c] += acc;
     }
     __syncthreads();
   }

@@ -162,7 +162,7 @@ __global__ void ln_dab_finish_kernel(const float* __restrict__ ws, float* __rest
   }
   for (; b < nblk; ++b) s[0] += ws[((long long)b * 2 + which) * D + col];
   float* dst = which == 0 ? da : db;
-  dst[col] += (s[0] + s[1]) + (s[2] + s[3]);
+  dst[col] = (s[0] + s[1]) + (s[2] + s[3]);      // overwritten: the caller hands in the gradient slot itself
 }
 
 template <typename T>

@@ -94,9 +94,38 @@ def gemm(A, B, Cout, M, N, K, *, nseg=1, nbatch=1, lda, ldb, ldc, transA=False, 
     L.check(L.lib().pka_gemm_f32(C.byref(d), L.stream_ptr()), "gemm_f32")
 
 
-def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+# ------------------------------------------------------------------------------------------------ gradient slots
+# FusedAdam keeps all gradients in one flat arena.  Backward kernels write a parameter's gradient straight into its
+# arena slot: the autograd Function returns a fresh view of the slot, AccumulateGrad (p.grad is None after
+# zero_grad) adopts that view instead of adding into a zeroed buffer -- no per-parameter `grad += g` kernels, no
+# arena memset.  Without a FusedAdam (or when p.grad already holds something to accumulate into) a plain buffer is used.
+_GRAD_SLOTS = {}
+
+
+def register_grad_slots(optimizer):
+    import weakref
+    ref = weakref.ref(optimizer)
+    for i, p in enumerate(optimizer._train):
+        _GRAD_SLOTS[p.data_ptr()] = (ref, i)
+
+
+def grad_buffer(param_like: torch.Tensor, shape=None) -> torch.Tensor:
+    """fp32 buffer for the gradient of the parameter `param_like` is (a view of): its arena slot when possible."""
+    shape = tuple(shape) if shape is not None else tuple(param_like.shape)
+    ent = _GRAD_SLOTS.get(param_like.data_ptr())
+    if ent is not None:
+        opt = ent[0]()
+        if opt is not None:
+            p = opt._train[ent[1]]
+            if p.grad is None and p.data_ptr() == param_like.data_ptr() and p.numel() == param_like.numel():
+                off = opt._offsets[ent[1]]
+                return opt.flat_grad[off:off + p.numel()].view(shape)
+    return torch.empty(shape, device=param_like.device, dtype=torch.float32)
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: Optional[bool] = None) -> torch.Tensor:
     rows, n = x2d.shape
-    acc = out is not None
+    acc = (out is not None) if accumulate is None else bool(accumulate)
     if out is None:
         out = torch.empty(n, device=x2d.device, dtype=torch.float32)
     chunks = L.lib().pka_colsum_chunks(C.c_int64(rows))
@@ -148,14 +177,14 @@ class _LinearFn(torch.autograd.Function):
             r2 = residual.reshape(M, N).contiguous()
         gemm(x2, w2, y, M, N, kin, nseg=n_ctx, lda=kin, ldb=n_ctx * kin, ldc=N, transB=True, b_seg_off=kin,
              shiftA=splice or (), T=T, bias=bias, relu=relu, drop=drop, residual=r2, ldr=N)
-        ctx.save_for_backward(x2, w2, y if relu else None)
+        ctx.save_for_backward(x2, w2, y if relu else None, bias)
         ctx.meta = (lead, kin, n_ctx, tuple(splice) if splice else (), T, relu, drop, bias is not None, weight.shape,
                     residual is not None)
         return y.view(*lead, N)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w2, y = ctx.saved_tensors
+        x2, w2, y, bias = ctx.saved_tensors
         lead, kin, n_ctx, splice, T, relu, drop, has_bias, wshape, has_res = ctx.meta
         M, N = x2.shape[0], w2.shape[0]
         dy2 = dy.reshape(M, N)
@@ -180,13 +209,13 @@ class _LinearFn(torch.autograd.Function):
                  shiftA=[-c for c in splice], T=T)
             dx = dx.view(*lead, kin)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty(N, n_ctx * kin, device=dy.device, dtype=torch.float32)
+            dw = grad_buffer(w2, (N, n_ctx * kin))
             # dW[o, s*kin + i] = sum_m dz[m,o] * x[m + ctx_s, i]   (batch over contexts, frame shift on the reduction index)
             gemm(dz, x2, dw, N, kin, M, nbatch=n_ctx, lda=N, ldb=kin, ldc=n_ctx * kin, transA=True, transB=False,
                  c_batch_off=kin, shiftB=splice, T=T)
             dw = dw.view(wshape)
         if has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dz)
+            db = colsum(dz, out=grad_buffer(bias), accumulate=False)
         dres = dy if (has_res and ctx.needs_input_grad[6]) else None
         return dx, dw, db, None, None, None, dres
 
@@ -258,13 +287,13 @@ class _HeadProjFn(torch.autograd.Function):
                 "head_weight_relayout")
         out = gemm_tc_rows(x, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.bfloat16)
         ctx.tc = True
-        ctx.save_for_backward(x, wd)
+        ctx.save_for_backward(x, wd, *ws)
         ctx.meta = (Bt, T, D, H, dk, P)
         return out
 
     @staticmethod
     def _backward_tc(ctx, dy):
-        x, wd = ctx.saved_tensors
+        x, wd, *ws = ctx.saved_tensors
         Bt, T, D, H, dk, P = ctx.meta
         ntot = P * H * dk
         dz = dy if (dy.dtype == torch.bfloat16 and dy.is_contiguous()) else gate_to_bf16(dy, Bt, T, ntot)
@@ -274,8 +303,7 @@ class _HeadProjFn(torch.autograd.Function):
         dws = [None] * P
         if any(ctx.needs_input_grad[1:1 + P]):
             dwcat = gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,))
-            dws = [torch.empty(H, D, dk, device=x.device, dtype=torch.float32) if ctx.needs_input_grad[1 + p] else None
-                   for p in range(P)]
+            dws = [grad_buffer(ws[p]) if ctx.needs_input_grad[1 + p] else None for p in range(P)]
             gp = [L.ptr(g) for g in dws] + [C.c_void_p(0)] * (3 - P)
             L.check(L.lib().pka_head_grad_relayout(L.ptr(dwcat), gp[0], gp[1], gp[2], P, H, D, dk, L.stream_ptr()),
                     "head_grad_relayout")
@@ -304,7 +332,7 @@ class _HeadProjFn(torch.autograd.Function):
             if not ctx.needs_input_grad[1 + p]:
                 dws.append(None)
                 continue
-            dw = torch.empty_like(w)
+            dw = grad_buffer(w)
             # dw_p[h,d,j] = sum_m x[m,d] * dy[m, p*H*dk + h*dk + j]
             gemm(x2, dy2, dw, D, dk, M, nbatch=H, lda=D, ldb=P * H * dk, ldc=dk, transA=True, transB=False,
                  b_batch_off=dk, c_batch_off=D * dk, b_ptr_off=p * H * dk)
@@ -471,21 +499,20 @@ class _AddLayerNormFn(torch.autograd.Function):
         L.check(L.lib().pka_add_layernorm_fwd(L.ptr(x2), L.ptr(r2), L.ptr(a), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rinv),
                                               L.dtype_code(x2), rows, D, C.c_float(eps), _byref_drop(drop), L.stream_ptr()),
                 "add_layernorm_fwd")
-        ctx.save_for_backward(x2, r2, a, mean, rinv)
+        ctx.save_for_backward(x2, r2, a, mean, rinv, b)
         ctx.meta = (shape, eps, drop)
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, r2, a, mean, rinv = ctx.saved_tensors
+        x2, r2, a, mean, rinv, b_par = ctx.saved_tensors
         shape, eps, drop = ctx.meta
         rows, D = x2.shape
         dy2 = dy.reshape(rows, D).contiguous()
         dres = torch.empty_like(x2)
         use_drop = drop is not None and drop.on
         dx = torch.empty_like(x2) if use_drop else None
-        da = torch.zeros(D, device=dy.device, dtype=torch.float32)
-        db = torch.zeros(D, device=dy.device, dtype=torch.float32)
+        da, db = grad_buffer(a), grad_buffer(b_par)                 # overwritten by the kernel
         nblk = L.lib().pka_ln_bwd_blocks(rows)
         ws = torch.empty(2 * D * nblk, device=dy.device, dtype=torch.float32)
         L.check(L.lib().pka_add_layernorm_bwd(L.ptr(dy2), L.ptr(x2), L.ptr(r2), L.ptr(a), L.ptr(mean), L.ptr(rinv), L.ptr(dx),
@@ -513,17 +540,17 @@ class _EmbedPosFn(torch.autograd.Function):
         out = torch.empty(B, Ln, D, device=emb.device, dtype=out_dtype)
         L.check(L.lib().pka_embed_pos_fwd(L.ptr(tok), L.ptr(emb), L.ptr(pos), L.ptr(out), L.dtype_code(out), B, Ln, D, V,
                                           _byref_drop(drop), L.stream_ptr()), "embed_pos_fwd")
-        ctx.save_for_backward(tok)
+        ctx.save_for_backward(tok, emb)
         ctx.meta = (V, D, drop, padding_idx)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (tok,) = ctx.saved_tensors
+        tok, emb = ctx.saved_tensors
         V, D, drop, padding_idx = ctx.meta
         B, Ln = tok.shape
         dout = dout.contiguous()
-        demb = torch.zeros(V, D, device=dout.device, dtype=torch.float32)
+        demb = grad_buffer(emb)                                      # every row is written by the kernel
         L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.dtype_code(dout), B, Ln, D, V, padding_idx,
                                       _byref_drop(drop), L.stream_ptr()), "embed_bwd")
         return None, demb, None, None, None, None
@@ -670,7 +697,7 @@ def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col
     return Cout
 
 
-def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None):
+def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None):
     """mode 2: dW[o, seg*N+i] = sum_{b,t} dZ[b,t,o] * X[b,t+shift[seg],i] -> fp32 [M, nseg*N], straight from the row-major
     activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
     split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic)."""
@@ -687,7 +714,7 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None):
     d.relu, d.c_dtype, d.splits = 0, L.PKA_F32, splits
     d.drop = L.NO_DROPOUT
     L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
-    acc = out is not None
+    acc = (out is not None) if accumulate is None else bool(accumulate)
     if out is None:
         out = torch.empty(M, nseg * N, device=dZ.device, dtype=torch.float32)
     L.check(L.lib().pka_tc_reduce(L.ptr(ws), L.ptr(out), C.c_int64(M * nseg * N), splits, int(acc), L.stream_ptr()), "tc_reduce")
@@ -729,13 +756,13 @@ class _LinearTcFn(torch.autograd.Function):
         wf, wd = weight_relayout(w2.detach(), kin, n_ctx, True, needs_dx)
         y = gemm_tc_rows(x, wf, Bt, T, N, kin, nseg=n_ctx, lda=kin, ldb=n_ctx * kin, b_seg_col=kin, shift=splice or (),
                          bias=bias, relu=relu, drop=drop, out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
-        ctx.save_for_backward(x, wd, y if relu else None)
+        ctx.save_for_backward(x, wd, y if relu else None, w2, bias)
         ctx.meta = (Bt, T, kin, N, n_ctx, tuple(splice) if splice else (0,), relu, drop, bias is not None, weight.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wd, y = ctx.saved_tensors
+        x, wd, y, w2, bias = ctx.saved_tensors
         Bt, T, kin, N, n_ctx, splice, relu, drop, has_bias, wshape = ctx.meta
         dy = dy.contiguous()
         use_drop = drop is not None and drop.on
@@ -754,9 +781,10 @@ class _LinearTcFn(torch.autograd.Function):
             dx = gemm_tc_rows(dz, wd, Bt, T, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * N, b_seg_col=N,
                               shift=[-c for c in splice])
         if ctx.needs_input_grad[1]:
-            dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice).view(wshape)
+            dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
+                               accumulate=False).view(wshape)
         if has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dz.view(Bt * T, N))
+            db = colsum(dz.view(Bt * T, N), out=grad_buffer(bias), accumulate=False)
         return dx, dw, db, None, None, None, None
 
 

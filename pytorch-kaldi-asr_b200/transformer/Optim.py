@@ -48,6 +48,8 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
             if self.flat_shadow is not None:
                 self.flat_shadow.copy_(self.flat_param)
+        from .. import ops as _ops
+        _ops.register_grad_slots(self)            # backward kernels write gradients straight into the arena slots
         self.dev_state = torch.zeros(2, device=dev, dtype=torch.int64)        # {adam_t, n_current_steps}
         self.dev_lr = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.use_device_lr = False                                            # switched on by ScheduledOptim
@@ -74,7 +76,14 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             p.grad = view
 
-    def zero_grad(self, set_to_none: bool = False):
+    def zero_grad(self, set_to_none: bool = True):
+        """Default: drop the .grad references (no kernel at all).  The next backward writes every gradient straight into
+        its arena slot and autograd adopts those views; `step()` zero-fills the slot of any parameter that got none.
+        set_to_none=False keeps torch's classic behaviour (one memset of the arena, gradients accumulate into it)."""
+        if set_to_none:
+            for p in self._train:
+                p.grad = None
+            return
         self._adopt_grads()
         self.flat_grad.zero_()
 

@@ -341,9 +341,15 @@ def test_fused_adam_matches_oracle_adam_and_schedule():
     for step in range(5):
         osch.step({str(i): g for i, g in enumerate(gs[step])})
         osch.update_learning_rate()
-        opt.zero_grad()
-        for p, g in zip(params, gs[step]):
-            p.grad.copy_(g.to(DEV))
+        if step % 2 == 0:                      # classic semantics: the arena is cleared, gradients are copied into the views
+            opt.optimizer.zero_grad(set_to_none=False)
+            for p, g in zip(params, gs[step]):
+                p.grad.copy_(g.to(DEV))
+        else:                                  # default: .grad dropped; a foreign gradient tensor is adopted into the arena
+            opt.zero_grad()
+            assert all(p.grad is None for p in params)
+            for p, g in zip(params, gs[step]):
+                p.grad = g.to(DEV)
         opt.step()
         opt.update_learning_rate()
     for i, p in enumerate(params):
