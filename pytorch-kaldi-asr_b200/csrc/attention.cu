@@ -3,8 +3,8 @@
 // of T/Models.py:27-49 are evaluated as an in-kernel predicate
 //        allowed(i,j) = key_mask[b,j] != 0  &&  (!band || i+start <= j <= i+end).
 // Rows with no allowed key produce 0 output / 0 gradient (the reference's post-softmax masked_fill, T/Modules.py:90).
-// Dropout on the probabilities: element (b,h,i,j) uses Philox index ((b*H+h)*Lq+i)*Lk4 + j with Lk4 = Lk rounded up to
-// a multiple of 4, so that four consecutive keys share one Philox call (the tensor-core kernel relies on this).
+// Dropout on the probabilities: element (b,h,i,j) uses Philox index ((b*H+h)*Lq+i)*Lk8 + j with Lk8 = Lk rounded up to
+// a multiple of 8, so that eight consecutive keys share one Philox call (the tensor-core kernels rely on this).
 // Tiles entirely outside the band are skipped, so the decoder's (-10,0) band costs O(L*11) instead of O(L^2).
 //
 // Layout: q[B,Lq,ldq], k[B,Lk,ldk], v[B,Lk,ldv], out[B,Lq,ldo]; head h occupies columns [h*D,(h+1)*D) -- the
@@ -89,7 +89,7 @@ attn_fwd_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict__ k,
     l_run = l_run * corr + warp_sum(pj);
     m_run = m_new;
     if (dc.p > 0.f && ok) {
-      unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 3) & ~3) + j;
+      unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 7) & ~7) + j;
       pj = dropout_keep(dc, idx) ? pj * dc.scale : 0.f;
     }
 #pragma unroll
@@ -180,7 +180,7 @@ attn_bwd_dq_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict__
       }
       const float pr = __expf(s * p.scale - lse_i);
       if (dc.p > 0.f) {
-        unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 3) & ~3) + j;
+        unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 7) & ~7) + j;
         dp = dropout_keep(dc, idx) ? dp * dc.scale : 0.f;
       }
       ds = pr * (dp - dl) * p.scale;
@@ -267,7 +267,7 @@ attn_bwd_dkv_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict_
       const float pr = __expf(s * p.scale - lse_i);
       float mul = 1.f;
       if (dc.p > 0.f) {
-        unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 3) & ~3) + j;
+        unsigned long long idx = (((unsigned long long)b * p.H + h) * p.Lq + i) * (unsigned long long)((p.Lk + 7) & ~7) + j;
         mul = dropout_keep(dc, idx) ? dc.scale : 0.f;
       }
       pd = pr * mul;                               // dropped probability: dV_j += pd * dO_i

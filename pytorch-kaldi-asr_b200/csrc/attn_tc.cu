@@ -128,7 +128,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const uint8_t* km = p.kmask + (long long)b * p.Lk;
     const DropCtx dc = make_drop(p.drop);
-    const unsigned long long drop_row = (((unsigned long long)b * p.H + h) * p.Lq + (row_ok ? i : 0)) * (unsigned long long)((p.Lk + 3) & ~3);
+    const unsigned long long drop_row = (((unsigned long long)b * p.H + h) * p.Lq + (row_ok ? i : 0)) * (unsigned long long)((p.Lk + 7) & ~7);
     float m_run = -CUDART_INF_F, l_run = 0.f;
     float o[AT_D];
 #pragma unroll
@@ -178,11 +178,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           l_tile += pe;
           pv[e] = pe;
         }
-        if (dc.p > 0.f && allow[c] != 0u) {        // one Philox call per 4 consecutive keys (row pitch Lk4 % 4 == 0)
+        if (dc.p > 0.f && allow[c] != 0u) {        // one Philox call per 8 consecutive keys (row pitch Lk8 % 8 == 0)
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 mul = dropout_mul4(dc, (drop_row + (unsigned long long)(j0 + c * 32 + e)) >> 2);
-            pv[e] *= mul.x; pv[e + 1] *= mul.y; pv[e + 2] *= mul.z; pv[e + 3] *= mul.w;
+          for (int e = 0; e < 32; e += 8) {
+            const uint32_t kb = dropout_bits8(dc, (drop_row + (unsigned long long)(j0 + c * 32 + e)) >> 3);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pv[e + u] = ((kb >> u) & 1u) ? pv[e + u] * dc.scale : 0.f;
           }
         }
         uint8_t* pblk = prow + (c >> 1) * (AT_BM * 128);
@@ -423,7 +424,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_const
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const uint8_t* km = p.kmask + (long long)b * p.Lk;
     const DropCtx dc = make_drop(p.drop);
-    const unsigned long long Lk4 = (unsigned long long)((p.Lk + 3) & ~3);
+    const unsigned long long Lk8 = (unsigned long long)((p.Lk + 7) & ~7);
     const unsigned long long bh = (unsigned long long)b * p.H + h;
     bool row_ok = x < Lrow;
     float row_lse2 = 0.f, row_del = 0.f;
@@ -500,25 +501,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_const
         tmem_ld_wait();
         float ds[32], pm[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          float mul[4] = {1.f, 1.f, 1.f, 1.f};
+        for (int e = 0; e < 32; e += 8) {
+          // keep bits of this thread's 8 (row, column) pairs
+          uint32_t kb = 0xffu;
           if (dc.p > 0.f) {
-            if (MODE == 0) {
-              const float4 m4 = dropout_mul4(dc, ((bh * p.Lq + x) * Lk4 + (unsigned long long)(c0 + c * 32 + e)) >> 2);
-              mul[0] = m4.x; mul[1] = m4.y; mul[2] = m4.z; mul[3] = m4.w;
+            if (MODE == 0) {                       // row = query: 8 consecutive keys share one Philox call
+              kb = dropout_bits8(dc, ((bh * p.Lq + x) * Lk8 + (unsigned long long)(c0 + c * 32 + e)) >> 3);
             } else {
+              // row = key x, columns = 8 consecutive queries.  A call covers 8 consecutive KEYS of one query, i.e. the 8
+              // lanes of an aligned lane group: lane L evaluates the call of query (e + (L & 7)) for its group's keys
+              // and the group exchanges the result bytes (8 shuffles instead of 8 Philox calls per thread).
+              const int qi = c0 + c * 32 + e + (lane & 7);
+              const uint32_t mine = dropout_bits8(dc, ((bh * p.Lq + (unsigned long long)qi) * Lk8 + (unsigned long long)(x & ~7)) >> 3);
+              kb = 0u;
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                mul[u] = dropout_keep(dc, (bh * p.Lq + (unsigned long long)(c0 + c * 32 + e + u)) * Lk4 + (unsigned long long)x) ? dc.scale : 0.f;
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t other = __shfl_sync(0xffffffffu, mine, (lane & ~7) | u);     // byte of query e+u, keys of my group
+                kb |= ((other >> (lane & 7)) & 1u) << u;
+              }
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int col = c * 32 + e + u;
             const float l2 = MODE == 0 ? row_lse2 : col_lse[(t & 1) * AB_BN + col];
             const float dl = MODE == 0 ? row_del : col_del[(t & 1) * AB_BN + col];
             const float pe = ((allow[c] >> (e + u)) & 1u) ? exp2f(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -l2)) : 0.f;
-            const float pmu = pe * mul[u];
+            const float pmu = ((kb >> u) & 1u) ? pe * dc.scale : 0.f;
             pm[e + u] = pmu;
             ds[e + u] = (pmu * __uint_as_float(dv[e + u]) - pe * dl) * p.scale;
           }

@@ -281,13 +281,17 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 2; ++c, ++w) {
             uint32_t bits = 0u;
+            if ((p.N & 7) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int nb = nb0 + c * 32 + j;
-              if (nb < p.N) {
-                const uint4 rnd = Philox::run(dc.seed, dc.site, dc.step, ((unsigned long long)m * p.N + nb) >> 2);
-                bits |= (rnd.x >= dc.thresh ? 1u : 0u) << j | (rnd.y >= dc.thresh ? 2u : 0u) << j |
-                        (rnd.z >= dc.thresh ? 4u : 0u) << j | (rnd.w >= dc.thresh ? 8u : 0u) << j;
+              for (int j = 0; j < 32; j += 8) {
+                const int nb = nb0 + c * 32 + j;
+                if (nb < p.N) bits |= dropout_bits8(dc, ((unsigned long long)m * p.N + nb) >> 3) << j;
+              }
+            } else {
+#pragma unroll 4
+              for (int j = 0; j < 32; ++j) {
+                const int nb = nb0 + c * 32 + j;
+                if (nb < p.N && dropout_keep(dc, (unsigned long long)m * p.N + nb)) bits |= 1u << j;
               }
             }
 #pragma unroll

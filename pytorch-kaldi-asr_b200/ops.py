@@ -671,9 +671,9 @@ def dropout_keep_mask(n: int, drop: Drop, device) -> torch.Tensor:
 
 def attn_keep_mask(B: int, H: int, Lq: int, Lk: int, drop: Drop, device) -> torch.Tensor:
     """Keep bits [B,H,Lq,Lk] of an attention-probability dropout site: the kernels index element (b,h,i,j) as
-    ((b*H+h)*Lq+i)*Lk4 + j with Lk4 = Lk rounded up to a multiple of 4 -- for parity tests only."""
-    Lk4 = (Lk + 3) // 4 * 4
-    return dropout_keep_mask(B * H * Lq * Lk4, drop, device).view(B, H, Lq, Lk4)[..., :Lk].contiguous()
+    ((b*H+h)*Lq+i)*Lk8 + j with Lk8 = Lk rounded up to a multiple of 8 -- for parity tests only."""
+    Lk8 = (Lk + 7) // 8 * 8
+    return dropout_keep_mask(B * H * Lq * Lk8, drop, device).view(B, H, Lq, Lk8)[..., :Lk].contiguous()
 
 
 # ================================================================================================ bf16 tensor-core path
