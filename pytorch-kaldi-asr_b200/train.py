@@ -36,14 +36,52 @@ def _to_device(batch, device, non_blocking=True):
     return put(batch[1], torch.float32), put(batch[2], torch.uint8), put(batch[3], torch.int64), put(batch[4], torch.uint8)
 
 
+class _Prefetcher:
+    """Host->device staging with one batch of look-ahead on a side stream (double buffering): `take()` hands out the
+    staged batch, `stage_next()` -- called right after the step's kernels have been launched and before any host
+    sync -- starts the H2D copies of the following batch so they overlap the running step (pinned host batches copy
+    asynchronously).  The reference copies synchronously inside the step (L/train.py:151-161)."""
+
+    def __init__(self, batch_loader, device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.it = iter(batch_loader)
+        self.staged = None
+        self.stage_next()
+
+    def stage_next(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self.staged = None
+            return
+        with torch.cuda.stream(self.copy_stream):
+            tensors = _to_device(batch, self.device)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.staged = (tensors, ev)
+
+    def take(self):
+        if self.staged is None:
+            return None
+        tensors, ev = self.staged
+        self.staged = None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for t in tensors:
+            t.record_stream(cur)
+        return tensors
+
+
 def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_eval=10, use_gpu=False, seq_error_prob=0,
-                smoothing=False, graphed: Optional["GraphedTrainStep"] = None):
+                smoothing=False, graphed: Optional["GraphedTrainStep"] = None, sync_every_step: bool = False):
     """One pass over `batch_loader` (L/train.py:127-214).  Returns (loss per word, token accuracy).
 
     Differences from the reference, all behaviour-preserving: the dead `use_seq_error` branches are not carried; the
     label-smoothing switch the reference hard-wires to False (L/train.py:193) is a keyword (default False); the three
-    running totals stay on the device and are read back once per epoch.  This path has no CPU mode: the model must be
-    on a CUDA device (`use_gpu` is accepted for signature compatibility)."""
+    running totals stay on the device and are read back once per epoch (`sync_every_step=True` reads them back after
+    every step like the reference does); host->device copies of batch i+1 overlap step i.  This path has no CPU mode: the
+    model must be on a CUDA device (`use_gpu` is accepted for signature compatibility)."""
     if mode == 'train':
         model.train()
         batch_loader.mode = 'drop'
@@ -57,11 +95,44 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
     if device.type != 'cuda':
         raise RuntimeError("train_epoch: the B200 path has no CPU mode; move the model to a CUDA device first")
     totals = torch.zeros(3, device=device, dtype=torch.float64)          # loss, n_correct, n_words
+    host_totals = [0.0, 0.0, 0.0]     # sync_every_step: the reference reads loss/accuracy back on every step (L/train.py:203-207)
 
-    for batch in batch_loader:
-        src_seq, src_pad_mask, tgt_seq, tgt_pad_mask = _to_device(batch, device)
+    feed = _Prefetcher(batch_loader, device)
+    # sync_every_step: each step's [loss, n_correct, n_words] is copied to pinned host memory right behind the step and
+    # consumed one step later, so the host never drains the GPU queue between steps
+    pinned = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)] if sync_every_step else None
+    pending, n_step = None, 0
+
+    def read_back(vec3):
+        nonlocal pending, n_step
+        buf = pinned[n_step % 2]
+        n_step += 1
+        buf.copy_(vec3, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        flush()
+        pending = (buf, ev)
+
+    def flush():
+        nonlocal pending
+        if pending is not None:
+            pending[1].synchronize()
+            for k, v in enumerate(pending[0].tolist()):
+                host_totals[k] += v
+            pending = None
+
+    while True:
+        cur = feed.take()
+        if cur is None:
+            break
+        src_seq, src_pad_mask, tgt_seq, tgt_pad_mask = cur
         if graphed is not None and mode == 'train':
-            totals += graphed.step(src_seq, src_pad_mask, tgt_seq, tgt_pad_mask).double()
+            out = graphed.step(src_seq, src_pad_mask, tgt_seq, tgt_pad_mask)
+            feed.stage_next()
+            if sync_every_step:
+                read_back(out)
+            else:
+                totals += out.double()
             continue
         goal = tgt_seq[:, 1:]
         tgt_in = tgt_seq[:, :-1]
@@ -77,13 +148,18 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
             loss.backward()
             optimizer.step()
             optimizer.update_learning_rate()
-        totals[0] += loss.detach().double()
-        totals[1:] += stats.double()
+        feed.stage_next()
+        if sync_every_step:
+            read_back(torch.cat([loss.detach().reshape(1), stats.reshape(2)]))
+        else:
+            totals[0] += loss.detach().double()
+            totals[1:] += stats.double()
         if mode == 'eval':
             seen += 1
             if seen == batch_eval:
                 break
-    loss_sum, n_correct, n_words = totals.tolist()
+    flush()
+    loss_sum, n_correct, n_words = [a + b for a, b in zip(totals.tolist(), host_totals)]
     return loss_sum / int(n_words), n_correct / int(n_words)
 
 
