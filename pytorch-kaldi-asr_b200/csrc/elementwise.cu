@@ -262,25 +262,41 @@ __global__ void transpose_kernel(const S* __restrict__ s, Dt* __restrict__ d, in
 }
 
 // ---------------------------------------------------------------------------------------------- optimiser
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, const float* __restrict__ lr_dev, float lr_host,
-                            const long long* __restrict__ state, float b1, float b2, float eps,
-                            __nv_bfloat16* __restrict__ shadow) {
-  const long long t = state[0] + 1;
-  const float lr = lr_dev ? lr_dev[0] : lr_host;
-  // bias corrections in double (torch computes them on the host in double precision)
-  const double bc1 = 1.0 - pow((double)b1, (double)t);
-  const double bc2 = 1.0 - pow((double)b2, (double)t);
-  const float step_size = (float)((double)lr / bc1);
-  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const float gv = g[e];
-    const float mv = b1 * m[e] + (1.f - b1) * gv;
-    const float vv = b2 * v[e] + (1.f - b2) * gv * gv;
-    m[e] = mv; v[e] = vv;
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, long long n, const float* __restrict__ lr_dev, float lr_host,
+            const long long* __restrict__ state, float b1, float b2, float eps,
+            __nv_bfloat16* __restrict__ shadow) {
+  __shared__ float s_step, s_isb2;
+  if (threadIdx.x == 0) {
+    // bias corrections in double, once per CTA (torch computes them on the host in double precision)
+    const long long t = state[0] + 1;
+    const float lr = lr_dev ? lr_dev[0] : lr_host;
+    const double bc1 = 1.0 - pow((double)b1, (double)t);
+    const double bc2 = 1.0 - pow((double)b2, (double)t);
+    s_step = (float)((double)lr / bc1);
+    s_isb2 = (float)(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step, inv_sqrt_bc2 = s_isb2;
+  auto upd = [&](float gv, float& mv, float& vv, float& pv) {
+    mv = b1 * mv + (1.f - b1) * gv;
+    vv = b2 * vv + (1.f - b2) * gv * gv;
     const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
-    const float pv = p[e] - step_size * (mv / denom);
-    p[e] = pv;
+    pv = pv - step_size * (mv / denom);
+  };
+  const long long n4 = n >> 2;                     // the arena is 16-byte aligned and padded to a multiple of 4
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 gv = reinterpret_cast<const float4*>(g)[e];
+    float4 mv = reinterpret_cast<float4*>(m)[e], vv = reinterpret_cast<float4*>(v)[e], pv = reinterpret_cast<float4*>(p)[e];
+    upd(gv.x, mv.x, vv.x, pv.x); upd(gv.y, mv.y, vv.y, pv.y); upd(gv.z, mv.z, vv.z, pv.z); upd(gv.w, mv.w, vv.w, pv.w);
+    reinterpret_cast<float4*>(m)[e] = mv; reinterpret_cast<float4*>(v)[e] = vv; reinterpret_cast<float4*>(p)[e] = pv;
+    if (shadow) st4(shadow + 4 * e, pv);
+  }
+  for (long long e = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float mv = m[e], vv = v[e], pv = p[e];
+    upd(g[e], mv, vv, pv);
+    m[e] = mv; v[e] = vv; p[e] = pv;
     if (shadow) shadow[e] = __float2bfloat16_rn(pv);
   }
 }
@@ -419,7 +435,8 @@ extern "C" int pka_adam_step(float* param, const float* grad, float* exp_avg, fl
                              void* bf16_shadow, void* stream) {
   PKA_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, PKA_EINVAL, "adam_step: bad arguments");
   cudaStream_t st = as_stream(stream);
-  adam_kernel<<<grid_for(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
+  PKA_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), PKA_EALIGN, "adam_step: the arenas must be 16-byte aligned");
+  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
   int rc = check_launch("adam");
   if (rc) return rc;
   adam_t_inc_kernel<<<1, 1, 0, st>>>((long long*)state);

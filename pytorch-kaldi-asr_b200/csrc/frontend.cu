@@ -9,29 +9,54 @@
 
 namespace pka {
 
-// stats[b][0][f] = mean, stats[b][1][f] = 1/sqrt(var) (or 1 when only the mean is removed)
+// stats[b][0][f] = mean, stats[b][1][f] = 1/sqrt(var) (or 1 when only the mean is removed).
+// One CTA per utterance.  The real frames of an utterance are one contiguous [n*F] run: a multiple of F/4 threads
+// streams it as float4 (fully coalesced) and every thread keeps hitting the SAME four features (its stride is a
+// multiple of F), so the per-feature sums live in registers (double) and meet once in shared memory, in thread order.
 __global__ void __launch_bounds__(256)
 cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths, float* __restrict__ stats, int T, int F,
                   int norm_vars) {
-  extern __shared__ double sm[];                  // [8 warps][2][F]
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ double sm[];                  // [256][8]: 4 sums + 4 sums of squares per thread
+  const int b = blockIdx.x, tid = threadIdx.x;
   int n = lengths[b];
   n = n < 0 ? 0 : (n > T ? T : n);
   const float* xb = x + (long long)b * T * F;
-  for (int f0 = 0; f0 < F; f0 += 32) {
-    const int f = f0 + lane;
-    double s = 0.0, s2 = 0.0;
-    if (f < F)
-      for (int t = warp; t < n; t += 8) { const double v = xb[(long long)t * F + f]; s += v; s2 += v * v; }
-    if (f < F) { sm[(warp * 2 + 0) * F + f] = s; sm[(warp * 2 + 1) * F + f] = s2; }
+  const bool vec = (F % 4 == 0) && F / 4 <= 256 && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  const int per = vec ? F / 4 : F;                // distinct column groups
+  const int nact = vec ? (256 / per) * per : (F <= 256 ? (256 / F) * F : 0);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (nact > 0 && tid < nact) {
+    if (vec) {
+      const long long n4 = (long long)n * F / 4;
+      auto acc = [&](const float4 v) {
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] += (double)v.x * v.x; q[1] += (double)v.y * v.y; q[2] += (double)v.z * v.z; q[3] += (double)v.w * v.w;
+      };
+      const float4* x4 = reinterpret_cast<const float4*>(xb);
+      long long e = tid;
+      for (; e + 3LL * nact < n4; e += 4LL * nact) {           // four independent loads in flight per thread
+        const float4 v0 = x4[e], v1 = x4[e + nact], v2 = x4[e + 2LL * nact], v3 = x4[e + 3LL * nact];
+        acc(v0); acc(v1); acc(v2); acc(v3);
+      }
+      for (; e < n4; e += nact) acc(x4[e]);
+    } else {
+      for (long long e = tid; e < (long long)n * F; e += nact) { const double v = xb[e]; s[0] += v; q[0] += v * v; }
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sm[tid * 8 + i] = s[i]; sm[tid * 8 + 4 + i] = q[i]; }
   __syncthreads();
-  for (int f = threadIdx.x; f < F; f += 256) {
-    double s = 0.0, s2 = 0.0;
-    for (int w = 0; w < 8; ++w) { s += sm[(w * 2 + 0) * F + f]; s2 += sm[(w * 2 + 1) * F + f]; }
-    double mean = n > 0 ? s / n : 0.0, istd = 1.0;
+  for (int f = tid; f < F; f += 256) {
+    double ss = 0.0, qq = 0.0;
+    if (nact > 0) {
+      const int grp = vec ? f / 4 : f, sub = vec ? f % 4 : 0;
+      for (int t = grp; t < nact; t += per) { ss += sm[t * 8 + sub]; qq += sm[t * 8 + 4 + sub]; }
+    } else {                                      // very wide features: plain strided pass
+      for (int t = 0; t < n; ++t) { const double v = xb[(long long)t * F + f]; ss += v; qq += v * v; }
+    }
+    double mean = n > 0 ? ss / n : 0.0, istd = 1.0;
     if (norm_vars && n > 0) {
-      double var = s2 / n - mean * mean;
+      double var = qq / n - mean * mean;
       if (var < 1e-20) var = 1e-20;
       istd = 1.0 / sqrt(var);
     }
@@ -45,26 +70,46 @@ struct FrontP {
   int ctx[PKA_MAX_CTX];
 };
 
+// One warp per output row (b, t): lane j owns output columns [VEC*j, VEC*j + VEC) (+ 32*VEC strides for wide rows), so
+// the column -> (context, frame-in-fold, feature) split is a handful of 32-bit operations and every access is one
+// 16-byte (fp32 in / bf16 out with VEC = 8) or 16-byte / 16-byte (VEC = 4, fp32 out) coalesced vector.
+// One thread per (output row, VEC-wide column group), all 32 lanes of every warp busy, two items in flight per thread.
+// The column-group -> (context shift, frame inside the fold, feature) split does not depend on the row: it is tabulated
+// once per CTA in shared memory, so an item costs two 32-bit divisions, one 16/32-byte load and one 16-byte store.
+constexpr int kFeMaxGroups = 1024;
 template <typename To, int VEC>
 __global__ void __launch_bounds__(256)
 frontend_kernel(const FrontP p, const float* __restrict__ x, const int* __restrict__ lengths,
                 const float* __restrict__ stats, To* __restrict__ out) {
+  __shared__ short g_shift[kFeMaxGroups], g_fr[kFeMaxGroups], g_f[kFeMaxGroups];
   const int Tf = p.T / p.fold, Ff = p.F * p.fold, W = p.n_ctx * Ff;
-  const long long total = (long long)p.B * Tf * (W / VEC);
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int col = (int)(e % (W / VEC)) * VEC;
-    const long long row = e / (W / VEC);
-    const int t = (int)(row % Tf), b = (int)(row / Tf);
-    const int c = col / Ff, fp = col % Ff;
-    const int ts = t + p.ctx[c];
+  const unsigned G = (unsigned)(W / VEC);
+  for (unsigned g = threadIdx.x; g < G; g += blockDim.x) {
+    const int col = (int)g * VEC, c = col / Ff, fp = col - c * Ff, fr = fp / p.F;
+    g_shift[g] = (short)p.ctx[c]; g_fr[g] = (short)fr; g_f[g] = (short)(fp - fr * p.F);   // VEC consecutive f share a frame
+  }
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)p.B * Tf * G;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  auto item = [&](unsigned long long idx) {
+    const unsigned row = (unsigned)(idx / G), g = (unsigned)(idx - (unsigned long long)row * G);
+    const unsigned b = row / (unsigned)Tf;
+    const int t = (int)(row - b * (unsigned)Tf);
+    const int ts = t + g_shift[g], f = g_f[g];
     float v[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) v[i] = 0.f;
     if (ts >= 0 && ts < Tf) {
-      const int frame = ts * p.fold + fp / p.F, f = fp % p.F;       // VEC consecutive f stay inside one frame (F%VEC==0)
+      const int frame = ts * p.fold + g_fr[g];
       const float* src = x + ((long long)b * p.T + frame) * p.F + f;
-      if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-      else v[0] = src[0];
+      if (VEC == 1) v[0] = src[0];
+      else {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(src + i);
+          v[i] = q.x; v[(i + 1) % VEC] = q.y; v[(i + 2) % VEC] = q.z; v[(i + 3) % VEC] = q.w;
+        }
+      }
       if (p.cmvn) {
         const bool real = frame < lengths[b];
         const float* mu = stats + ((long long)b * 2 + 0) * p.F + f;
@@ -73,10 +118,22 @@ frontend_kernel(const FrontP p, const float* __restrict__ x, const int* __restri
         for (int i = 0; i < VEC; ++i) v[i] = real ? (v[i] - mu[i]) * is[i] : 0.f;
       }
     }
-    To* dst = out + row * W + col;
-    if (VEC == 4) st4(dst, make_float4(v[0], v[1], v[2], v[3]));
-    else dst[0] = from_f<To>(v[0]);
-  }
+    To* dst = out + (long long)row * W + g * VEC;
+    if (VEC == 1) dst[0] = from_f<To>(v[0]);
+    else if (VEC == 8 && sizeof(To) == 2) {        // one 16-byte store of 8 bf16
+      uint4 pk;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1 % VEC]), h1 = __floats2bfloat162_rn(v[2 % VEC], v[3 % VEC]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4 % VEC], v[5 % VEC]), h3 = __floats2bfloat162_rn(v[6 % VEC], v[7 % VEC]);
+      pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+      *reinterpret_cast<uint4*>(dst) = pk;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) st4(dst + i, make_float4(v[i], v[(i + 1) % VEC], v[(i + 2) % VEC], v[(i + 3) % VEC]));
+    }
+  };
+  unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  for (; idx + stride < total; idx += 2 * stride) { item(idx); item(idx + stride); }
+  if (idx < total) item(idx);
 }
 
 }  // namespace pka
@@ -92,24 +149,27 @@ extern "C" int pka_frontend_fwd(const float* feats, const int32_t* lengths, void
   PKA_REQUIRE(cmvn_mode == 0 || (lengths && stats_ws), PKA_EINVAL, "frontend_fwd: CMVN needs lengths and stats_ws");
   cudaStream_t st = as_stream(stream);
   if (cmvn_mode) {
-    cmvn_stats_kernel<<<B, 256, 8 * 2 * F * sizeof(double), st>>>(feats, lengths, stats_ws, T, F, cmvn_mode == 2);
+    cmvn_stats_kernel<<<B, 256, 256 * 8 * sizeof(double), st>>>(feats, lengths, stats_ws, T, F, cmvn_mode == 2);
     int rc = check_launch("cmvn_stats");
     if (rc) return rc;
   }
   FrontP p;
   p.B = B; p.T = T; p.F = F; p.fold = fold; p.n_ctx = n_ctx; p.cmvn = cmvn_mode;
   for (int i = 0; i < PKA_MAX_CTX; ++i) p.ctx[i] = i < n_ctx ? ctx_host[i] : 0;
-  const bool vec = (F % 4 == 0) && aligned16(feats) && aligned16(out);
   const long long W = (long long)n_ctx * F * fold;
-  const long long total = (long long)B * (T / fold) * (vec ? W / 4 : W);
-  long long blocks = (total + 255) / 256;
+  PKA_REQUIRE(W <= kFeMaxGroups, PKA_EUNSUPPORTED, "frontend_fwd: spliced row width %lld exceeds %d", W, kFeMaxGroups);
+  const long long items = (long long)B * (T / fold) * (W / 4);
+  long long blocks = (items + 511) / 512;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  if (blocks < 1) blocks = 1;
+  const bool v4 = (F % 4 == 0) && aligned16(feats) && aligned16(out);
+  const bool v8 = v4 && (F % 8 == 0);
+#define PKA_FE(To, V) frontend_kernel<To, V><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (To*)out)
   if (out_dtype == PKA_F32) {
-    if (vec) frontend_kernel<float, 4><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (float*)out);
-    else frontend_kernel<float, 1><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (float*)out);
+    if (v4) PKA_FE(float, 4); else PKA_FE(float, 1);
   } else if (out_dtype == PKA_BF16) {
-    if (vec) frontend_kernel<__nv_bfloat16, 4><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (__nv_bfloat16*)out);
-    else frontend_kernel<__nv_bfloat16, 1><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (__nv_bfloat16*)out);
+    if (v8) PKA_FE(__nv_bfloat16, 8); else if (v4) PKA_FE(__nv_bfloat16, 4); else PKA_FE(__nv_bfloat16, 1);
   } else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "frontend_fwd: out dtype %d", out_dtype);
+#undef PKA_FE
   return check_launch("frontend");
 }

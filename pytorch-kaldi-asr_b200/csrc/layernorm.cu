@@ -8,8 +8,50 @@ namespace pka {
 
 constexpr int kLnWarps = 8;
 
-// VPL = float4 vectors per lane; a row of D = up to 128*VPL elements lives in registers.
-template <typename T, int VPL>
+// EV consecutive elements (one 16-byte vector: 4 fp32 or 8 bf16) <-> registers
+template <typename T, int EV> __device__ __forceinline__ void ldv(const T* p, float (&v)[EV]);
+template <> __device__ __forceinline__ void ldv<float, 4>(const float* p, float (&v)[4]) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 4>(const __nv_bfloat16* p, float (&v)[4]) {
+  const float4 q = ld4(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 8>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T, int EV> __device__ __forceinline__ void stv(T* p, const float (&v)[EV]);
+template <> __device__ __forceinline__ void stv<float, 4>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&v)[4]) {
+  st4(p, make_float4(v[0], v[1], v[2], v[3]));
+}
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 8>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+// dropout multipliers of EV consecutive elements starting at element index e0 (e0 % EV == 0)
+template <int EV> __device__ __forceinline__ void drop_mulv(const DropCtx& dc, unsigned long long e0, float (&m)[EV]) {
+  if (EV == 8) {
+    const uint32_t b = dropout_bits8(dc, e0 >> 3);
+#pragma unroll
+    for (int i = 0; i < EV; ++i) m[i] = ((b >> i) & 1u) ? dc.scale : 0.f;
+  } else {
+    const float4 q = dropout_mul4(dc, e0 >> 2);
+    m[0] = q.x; m[1] = q.y; m[2] = q.z; m[3] = q.w;
+  }
+}
+
+// VPL = 16-byte vectors per lane (EV elements each); a row of D <= 32*EV*VPL elements lives in registers.
+template <typename T, int EV, int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ a,
                   const float* __restrict__ bta, T* __restrict__ y, float* __restrict__ mean_o,
@@ -20,31 +62,39 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
   DropCtx dc = make_drop(drop);
   const T* xr = x + (long long)row * D;
   const T* rr = res ? res + (long long)row * D : nullptr;
-  float4 z[VPL];
+  float z[VPL][EV];
   float sum = 0.f;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * 4;
-    z[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (v * 32 + lane) * EV;
+#pragma unroll
+    for (int i = 0; i < EV; ++i) z[v][i] = 0.f;
     if (c < D) {
-      float4 xv = ld4(xr + c);
+      ldv<T, EV>(xr + c, z[v]);
       if (dc.p > 0.f) {
-        float4 m = dropout_mul4(dc, ((unsigned long long)row * D + c) >> 2);
-        xv.x *= m.x; xv.y *= m.y; xv.z *= m.z; xv.w *= m.w;
+        float m[EV];
+        drop_mulv<EV>(dc, (unsigned long long)row * D + c, m);
+#pragma unroll
+        for (int i = 0; i < EV; ++i) z[v][i] *= m[i];
       }
-      if (rr) { float4 rv = ld4(rr + c); xv.x += rv.x; xv.y += rv.y; xv.z += rv.z; xv.w += rv.w; }
-      z[v] = xv;
-      sum += (xv.x + xv.y) + (xv.z + xv.w);
+      if (rr) {
+        float r[EV];
+        ldv<T, EV>(rr + c, r);
+#pragma unroll
+        for (int i = 0; i < EV; ++i) z[v][i] += r[i];
+      }
+#pragma unroll
+      for (int i = 0; i < EV; ++i) sum += z[v][i];
     }
   }
   const float mean = warp_sum(sum) / (float)D;
   float sq = 0.f;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * 4;
+    const int c = (v * 32 + lane) * EV;
     if (c < D) {
-      float dx = z[v].x - mean, dy = z[v].y - mean, dz = z[v].z - mean, dw = z[v].w - mean;
-      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+      for (int i = 0; i < EV; ++i) { const float d = z[v][i] - mean; sq = fmaf(d, d, sq); }
     }
   }
   const float sigma = sqrtf(warp_sum(sq) / (float)(D - 1));
@@ -52,35 +102,41 @@ add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const floa
   T* yr = y + (long long)row * D;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * 4;
+    const int c = (v * 32 + lane) * EV;
     if (c < D) {
-      const float4 av = *reinterpret_cast<const float4*>(a + c);
-      const float4 bv = *reinterpret_cast<const float4*>(bta + c);
-      float4 o;
-      o.x = (z[v].x - mean) * rinv * av.x + bv.x;
-      o.y = (z[v].y - mean) * rinv * av.y + bv.y;
-      o.z = (z[v].z - mean) * rinv * av.z + bv.z;
-      o.w = (z[v].w - mean) * rinv * av.w + bv.w;
-      st4(yr + c, o);
+      float o[EV];
+#pragma unroll
+      for (int i = 0; i < EV; i += 4) {
+        const float4 av = *reinterpret_cast<const float4*>(a + c + i);
+        const float4 bv = *reinterpret_cast<const float4*>(bta + c + i);
+        o[i] = (z[v][i] - mean) * rinv * av.x + bv.x;
+        o[i + 1] = (z[v][i + 1] - mean) * rinv * av.y + bv.y;
+        o[i + 2] = (z[v][i + 2] - mean) * rinv * av.z + bv.z;
+        o[i + 3] = (z[v][i + 3] - mean) * rinv * av.w + bv.w;
+      }
+      stv<T, EV>(yr + c, o);
     }
   }
   if (lane == 0) { mean_o[row] = mean; rinv_o[row] = rinv; }
 }
 
 // backward: dz_i = rinv*(g_i - mean(g)) - c_i * rinv^2 * sum(g*c) / ((D-1)*sigma),  g = dy*a, c = z-mean
-//           dres = dz,  dx = keep*dz/(1-p),  da += sum_rows dy*c*rinv,  db += sum_rows dy
-template <typename T, int VPL>
+//           dres = dz,  dx = keep*dz/(1-p),  da = sum_rows dy*c*rinv,  db = sum_rows dy
+template <typename T, int EV, int VPL>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                   const float* __restrict__ a, const float* __restrict__ mean_i, const float* __restrict__ rinv_i,
                   T* __restrict__ dx, T* __restrict__ dres, float* __restrict__ dab_ws, int rows, int D, float eps,
                   const pka_dropout drop) {
-  __shared__ float red[kLnWarps][2][128 * VPL];
+  __shared__ float red[kLnWarps][2][32 * EV * VPL];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DropCtx dc = make_drop(drop);
-  float4 da_acc[VPL], db_acc[VPL];
+  float da_acc[VPL][EV], db_acc[VPL][EV];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) { da_acc[v] = make_float4(0, 0, 0, 0); db_acc[v] = make_float4(0, 0, 0, 0); }
+  for (int v = 0; v < VPL; ++v) {
+#pragma unroll
+    for (int i = 0; i < EV; ++i) { da_acc[v][i] = 0.f; db_acc[v][i] = 0.f; }
+  }
 
   for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
     const float mean = mean_i[row], rinv = rinv_i[row];
@@ -88,28 +144,43 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     const T* xr = x + (long long)row * D;
     const T* rr = res ? res + (long long)row * D : nullptr;
     const T* gr = dy + (long long)row * D;
-    float4 c[VPL], g[VPL], keep[VPL];
+    float c[VPL][EV], g[VPL][EV], keep[VPL][EV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const int col = (v * 32 + lane) * 4;
-      c[v] = make_float4(0, 0, 0, 0); g[v] = c[v]; keep[v] = make_float4(1, 1, 1, 1);
+      const int col = (v * 32 + lane) * EV;
+#pragma unroll
+      for (int i = 0; i < EV; ++i) { c[v][i] = 0.f; g[v][i] = 0.f; keep[v][i] = 1.f; }
       if (col < D) {
-        float4 xv = ld4(xr + col);
+        float xv[EV], dyv[EV];
+        ldv<T, EV>(xr + col, xv);
+        ldv<T, EV>(gr + col, dyv);
         if (dc.p > 0.f) {
-          keep[v] = dropout_mul4(dc, ((unsigned long long)row * D + col) >> 2);
-          xv.x *= keep[v].x; xv.y *= keep[v].y; xv.z *= keep[v].z; xv.w *= keep[v].w;
+          drop_mulv<EV>(dc, (unsigned long long)row * D + col, keep[v]);
+#pragma unroll
+          for (int i = 0; i < EV; ++i) xv[i] *= keep[v][i];
         }
-        if (rr) { float4 rv = ld4(rr + col); xv.x += rv.x; xv.y += rv.y; xv.z += rv.z; xv.w += rv.w; }
-        c[v] = make_float4(xv.x - mean, xv.y - mean, xv.z - mean, xv.w - mean);
-        const float4 dyv = ld4(gr + col);
-        const float4 av = *reinterpret_cast<const float4*>(a + col);
-        g[v] = make_float4(dyv.x * av.x, dyv.y * av.y, dyv.z * av.z, dyv.w * av.w);
-        s1 += (g[v].x + g[v].y) + (g[v].z + g[v].w);
-        s2 += (g[v].x * c[v].x + g[v].y * c[v].y) + (g[v].z * c[v].z + g[v].w * c[v].w);
-        da_acc[v].x += dyv.x * c[v].x * rinv; da_acc[v].y += dyv.y * c[v].y * rinv;
-        da_acc[v].z += dyv.z * c[v].z * rinv; da_acc[v].w += dyv.w * c[v].w * rinv;
-        db_acc[v].x += dyv.x; db_acc[v].y += dyv.y; db_acc[v].z += dyv.z; db_acc[v].w += dyv.w;
+        if (rr) {
+          float rv[EV];
+          ldv<T, EV>(rr + col, rv);
+#pragma unroll
+          for (int i = 0; i < EV; ++i) xv[i] += rv[i];
+        }
+        float av[EV];                              // L1-resident gain vector (kept out of the loop-carried registers)
+#pragma unroll
+        for (int i = 0; i < EV; i += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(a + col + i);
+          av[i] = q.x; av[i + 1] = q.y; av[i + 2] = q.z; av[i + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < EV; ++i) {
+          c[v][i] = xv[i] - mean;
+          g[v][i] = dyv[i] * av[i];
+          s1 += g[v][i];
+          s2 = fmaf(g[v][i], c[v][i], s2);
+          da_acc[v][i] = fmaf(dyv[i] * c[v][i], rinv, da_acc[v][i]);
+          db_acc[v][i] += dyv[i];
+        }
       }
     }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -117,17 +188,16 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
     const float kf = sigma > 0.f ? rinv * rinv * s2 / ((float)(D - 1) * sigma) : 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const int col = (v * 32 + lane) * 4;
+      const int col = (v * 32 + lane) * EV;
       if (col < D) {
-        float4 dz;
-        dz.x = rinv * (g[v].x - gm) - c[v].x * kf;
-        dz.y = rinv * (g[v].y - gm) - c[v].y * kf;
-        dz.z = rinv * (g[v].z - gm) - c[v].z * kf;
-        dz.w = rinv * (g[v].w - gm) - c[v].w * kf;
-        if (dres) st4(dres + (long long)row * D + col, dz);
+        float dz[EV];
+#pragma unroll
+        for (int i = 0; i < EV; ++i) dz[i] = rinv * (g[v][i] - gm) - c[v][i] * kf;
+        if (dres) stv<T, EV>(dres + (long long)row * D + col, dz);
         if (dx) {
-          dz.x *= keep[v].x; dz.y *= keep[v].y; dz.z *= keep[v].z; dz.w *= keep[v].w;
-          st4(dx + (long long)row * D + col, dz);
+#pragma unroll
+          for (int i = 0; i < EV; ++i) dz[i] *= keep[v][i];
+          stv<T, EV>(dx + (long long)row * D + col, dz);
         }
       }
     }
@@ -135,9 +205,9 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   // CTA-level reduction of the per-warp column sums, then one partial row per CTA (summed by the finish kernel)
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
-    const int col = (v * 32 + lane) * 4;
-    *reinterpret_cast<float4*>(&red[warp][0][col]) = da_acc[v];
-    *reinterpret_cast<float4*>(&red[warp][1][col]) = db_acc[v];
+    const int col = (v * 32 + lane) * EV;
+#pragma unroll
+    for (int i = 0; i < EV; ++i) { red[warp][0][col + i] = da_acc[v][i]; red[warp][1][col + i] = db_acc[v][i]; }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * D; e += kLnWarps * 32) {
@@ -149,29 +219,46 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   }
 }
 
-__global__ void ln_dab_finish_kernel(const float* __restrict__ ws, float* __restrict__ da, float* __restrict__ db,
-                                     int nblk, int D) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 2 * D) return;
-  const int which = e / D, col = e % D;
+// da[col] / db[col] = sum over the per-CTA partial rows: a CTA owns 32 columns of one of the two vectors, its 8 warps
+// take interleaved partial rows (coalesced 128 B reads), fixed-order combine through shared memory (deterministic)
+__global__ void __launch_bounds__(256)
+ln_dab_finish_kernel(const float* __restrict__ ws, float* __restrict__ da, float* __restrict__ db, int nblk, int D) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cols32 = (D + 31) / 32;
+  const int which = blockIdx.x / cols32, col = (blockIdx.x % cols32) * 32 + lane;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  int b = 0;
-  for (; b + 4 <= nblk; b += 4) {
+  if (col < D) {
+    int b = w;
+    for (; b + 24 < nblk; b += 32) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] += ws[((long long)(b + u) * 2 + which) * D + col];
+      for (int u = 0; u < 4; ++u) s[u] += ws[((long long)(b + 8 * u) * 2 + which) * D + col];
+    }
+    for (; b < nblk; b += 8) s[0] += ws[((long long)b * 2 + which) * D + col];
   }
-  for (; b < nblk; ++b) s[0] += ws[((long long)b * 2 + which) * D + col];
-  float* dst = which == 0 ? da : db;
-  dst[col] = (s[0] + s[1]) + (s[2] + s[3]);      // overwritten: the caller hands in the gradient slot itself
+  red[w][lane] = (s[0] + s[1]) + (s[2] + s[3]);
+  __syncthreads();
+  if (w == 0 && col < D) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    (which == 0 ? da : db)[col] = t;               // overwritten: the caller hands in the gradient slot itself
+  }
 }
 
 template <typename T>
 static int fwd_t(const void* x, const void* res, const float* a, const float* b, void* y, float* mean, float* rinv,
                  int rows, int D, float eps, const pka_dropout& dr, cudaStream_t st) {
   dim3 grid((rows + kLnWarps - 1) / kLnWarps), block(kLnWarps * 32);
-  const int vpl = (D + 127) / 128;
-#define LN_FWD(V) add_ln_fwd_kernel<T, V><<<grid, block, 0, st>>>((const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
-  if (vpl <= 1) LN_FWD(1); else if (vpl <= 2) LN_FWD(2); else if (vpl <= 4) LN_FWD(4); else LN_FWD(8);
+#define LN_FWD(E, V) add_ln_fwd_kernel<T, E, V><<<grid, block, 0, st>>>((const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
+  if (sizeof(T) == 2 && D % 8 == 0) {             // bf16: 8 elements (16 bytes) per lane and vector
+    constexpr int E = sizeof(T) == 2 ? 8 : 4;
+    const int vpl = (D + 255) / 256;
+    if (vpl <= 1) LN_FWD(E, 1); else if (vpl <= 2) LN_FWD(E, 2); else LN_FWD(E, 4);
+  } else {
+    const int vpl = (D + 127) / 128;
+    if (vpl <= 1) LN_FWD(4, 1); else if (vpl <= 2) LN_FWD(4, 2); else if (vpl <= 4) LN_FWD(4, 4); else LN_FWD(4, 8);
+  }
 #undef LN_FWD
   return check_launch("add_layernorm_fwd");
 }
@@ -182,13 +269,19 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
                  const pka_dropout& dr, cudaStream_t st) {
   const int nblk = pka_ln_bwd_blocks(rows);
   dim3 grid(nblk), block(kLnWarps * 32);
-  const int vpl = (D + 127) / 128;
-#define LN_BWD(V) add_ln_bwd_kernel<T, V><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)res, a, mean, rinv, (T*)dx, (T*)dres, ws, rows, D, eps, dr)
-  if (vpl <= 1) LN_BWD(1); else if (vpl <= 2) LN_BWD(2); else LN_BWD(4);
+#define LN_BWD(E, V) add_ln_bwd_kernel<T, E, V><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)res, a, mean, rinv, (T*)dx, (T*)dres, ws, rows, D, eps, dr)
+  if (sizeof(T) == 2 && D % 8 == 0) {
+    constexpr int E = sizeof(T) == 2 ? 8 : 4;
+    const int vpl = (D + 255) / 256;
+    if (vpl <= 1) LN_BWD(E, 1); else LN_BWD(E, 2);
+  } else {
+    const int vpl = (D + 127) / 128;
+    if (vpl <= 1) LN_BWD(4, 1); else if (vpl <= 2) LN_BWD(4, 2); else LN_BWD(4, 4);
+  }
 #undef LN_BWD
   int rc = check_launch("add_layernorm_bwd");
   if (rc) return rc;
-  ln_dab_finish_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(ws, da, db, nblk, D);
+  ln_dab_finish_kernel<<<2 * ((D + 31) / 32), 256, 0, st>>>(ws, da, db, nblk, D);
   return check_launch("ln_dab_finish");
 }
 
@@ -197,7 +290,7 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
 extern "C" int pka_ln_bwd_blocks(int rows) {
   int need = (rows + pka::kLnWarps - 1) / pka::kLnWarps;
   // few partial rows keep the fixed-order finish short (small decoder tensors); one CTA per SM for large ones
-  int cap = rows <= 8192 ? 64 : pka::kNumSMs;
+  int cap = rows <= 8192 ? 64 : pka::kNumSMs * 8;  // enough resident warps to pull HBM bandwidth on large tensors
   return need < cap ? (need > 0 ? need : 1) : cap;
 }
 
