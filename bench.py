@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -73,7 +73,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
+        self.proc.kill()                   # make sure the poller is gone before the next timed region starts
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -440,6 +444,9 @@ def run_b200(args):
             for i in range(args.warmup):
                 step_fn(i)
         barrier()
+        import gc
+        gc.collect()
+        gc.disable()                              # no collector pauses inside the timed region
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.launch_count()
         s.record()
@@ -450,6 +457,7 @@ def run_b200(args):
                 step_fn(args.warmup + i)
         e.record()
         barrier()
+        gc.enable()
         ms = s.elapsed_time(e)
         frames = sum(frames_pool[(args.warmup + i) % n_pool] for i in range(args.steps))
         t = torch.tensor([ms, float(frames)], device="cuda", dtype=torch.float64)

@@ -40,6 +40,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(kAttWarps * 32)
 attn_fwd_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                 const uint8_t* __restrict__ kmask, T* __restrict__ out, float* __restrict__ lse) {
+  pdl_wait();
   constexpr int R = D / 32 > 0 ? D / 32 : 1;       // output columns per lane
   __shared__ float Ks[kAttTile][D + 1];
   __shared__ float Vs[kAttTile][D];
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kAttWarps * 32)
 attn_bwd_dq_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                    const uint8_t* __restrict__ kmask, const T* __restrict__ out, const T* __restrict__ dout,
                    const float* __restrict__ lse, float* __restrict__ delta, T* __restrict__ dq) {
+  pdl_wait();
   constexpr int R = D / 32 > 0 ? D / 32 : 1;
   __shared__ float Ks[kAttTile][D + 1];
   __shared__ float Vs[kAttTile][D + 1];
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(kAttWarps * 32)
 attn_bwd_dkv_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                     const uint8_t* __restrict__ kmask, const T* __restrict__ dout, const float* __restrict__ lse,
                     const float* __restrict__ delta, T* __restrict__ dk, T* __restrict__ dv) {
+  pdl_wait();
   constexpr int R = D / 32 > 0 ? D / 32 : 1;
   __shared__ float Qt[kAttTile][D + 1];
   __shared__ float dOt[kAttTile][D + 1];
@@ -303,6 +306,7 @@ template <typename T>
 __global__ void attn_probs_kernel(const AttnP p, int D, const T* __restrict__ q, const T* __restrict__ k,
                                   const uint8_t* __restrict__ kmask, const float* __restrict__ lse,
                                   float* __restrict__ probs) {
+  pdl_wait();
   const long long total = (long long)p.B * p.H * p.Lq * p.Lk;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int j = e % p.Lk;
@@ -347,11 +351,11 @@ template <typename T>
 static int fwd_t(const AttnP& p, int D, const void* q, const void* k, const void* v, const uint8_t* km, void* out,
                  float* lse, float* probs, cudaStream_t st) {
   dim3 grid((p.Lq + kAttWarps - 1) / kAttWarps, p.H, p.B), block(kAttWarps * 32);
-  PKA_ATT_DISPATCH(D, (attn_fwd_kernel<T, DD><<<grid, block, 0, st>>>(p, (const T*)q, (const T*)k, (const T*)v, km, (T*)out, lse)));
+  PKA_ATT_DISPATCH(D, (launch_k(attn_fwd_kernel<T, DD>, grid, block, 0, st, p, (const T*)q, (const T*)k, (const T*)v, km, (T*)out, lse)));
   int rc = check_launch("attn_fwd");
   if (rc) return rc;
   if (probs) {
-    attn_probs_kernel<T><<<kNumSMs * 4, 256, 0, st>>>(p, D, (const T*)q, (const T*)k, km, lse, probs);
+    launch_k(attn_probs_kernel<T>, kNumSMs * 4, 256, 0, st, p, D, (const T*)q, (const T*)k, km, lse, probs);
     rc = check_launch("attn_probs");
   }
   return rc;
@@ -363,11 +367,11 @@ static int bwd_t(const AttnP& p, int D, const void* q, const void* k, const void
                  cudaStream_t st) {
   dim3 block(kAttWarps * 32);
   dim3 gq((p.Lq + kAttWarps - 1) / kAttWarps, p.H, p.B);
-  PKA_ATT_DISPATCH(D, (attn_bwd_dq_kernel<T, DD><<<gq, block, 0, st>>>(p, (const T*)q, (const T*)k, (const T*)v, km, (const T*)out, (const T*)dout, lse, delta, (T*)dq)));
+  PKA_ATT_DISPATCH(D, (launch_k(attn_bwd_dq_kernel<T, DD>, gq, block, 0, st, p, (const T*)q, (const T*)k, (const T*)v, km, (const T*)out, (const T*)dout, lse, delta, (T*)dq)));
   int rc = check_launch("attn_bwd_dq");
   if (rc) return rc;
   dim3 gk((p.Lk + kAttWarps - 1) / kAttWarps, p.H, p.B);
-  PKA_ATT_DISPATCH(D, (attn_bwd_dkv_kernel<T, DD><<<gk, block, 0, st>>>(p, (const T*)q, (const T*)k, (const T*)v, km, (const T*)dout, lse, delta, (T*)dk, (T*)dv)));
+  PKA_ATT_DISPATCH(D, (launch_k(attn_bwd_dkv_kernel<T, DD>, gk, block, 0, st, p, (const T*)q, (const T*)k, (const T*)v, km, (const T*)dout, lse, delta, (T*)dk, (T*)dv)));
   return check_launch("attn_bwd_dkv");
 }
 

@@ -78,6 +78,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // the prologue above touched only shared / tensor memory
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
   if (warp == 4) {
@@ -274,7 +275,7 @@ extern "C" int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = out; p.lse = lse; p.kmask = key_mask; p.drop = d->drop;
   dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->H, d->B);
-  attn_tc_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, as_stream(stream)>>>(mapQ, mapK, mapV, p);
+  launch_k(attn_tc_fwd_kernel, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
   return check_launch("attn_tc_fwd");
 }
 
@@ -369,6 +370,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // the prologue above touched only shared / tensor memory
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_A0 = tmem_base + 128, tmem_A1 = tmem_base + 192;
 
   if (warp == 4) {
@@ -624,11 +626,11 @@ extern "C" int pka_attn_tc_bwd(const pka_attn_desc* d, const void* q, const void
   p.drop = d->drop;
   p.g0 = (__nv_bfloat16*)dq; p.ldg0 = d->ldq; p.g1 = nullptr; p.ldg1 = 0;
   dim3 gq((d->Lq + AB_BM - 1) / AB_BM, d->H, d->B);
-  attn_tc_bwd_kernel<0><<<gq, AT_THREADS, AB_SMEM, as_stream(stream)>>>(mQr, mDOr, mKc, mVc, p);
+  launch_k(attn_tc_bwd_kernel<0>, gq, AT_THREADS, AB_SMEM, as_stream(stream), mQr, mDOr, mKc, mVc, p);
   rc = check_launch("attn_tc_bwd(dq)");
   if (rc) return rc;
   p.g0 = (__nv_bfloat16*)dk; p.ldg0 = d->ldk; p.g1 = (__nv_bfloat16*)dv; p.ldg1 = d->ldv;
   dim3 gk((d->Lk + AB_BM - 1) / AB_BM, d->H, d->B);
-  attn_tc_bwd_kernel<1><<<gk, AT_THREADS, AB_SMEM, as_stream(stream)>>>(mKr, mVr, mQc, mDOc, p);
+  launch_k(attn_tc_bwd_kernel<1>, gk, AT_THREADS, AB_SMEM, as_stream(stream), mKr, mVr, mQc, mDOc, p);
   return check_launch("attn_tc_bwd(dkv)");
 }

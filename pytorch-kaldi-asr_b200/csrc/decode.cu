@@ -22,6 +22,7 @@ __global__ void beam_embed_kernel(const float* __restrict__ emb, const float* __
                                   const int* __restrict__ edge_word, const int* __restrict__ edge_depth,
                                   const int* __restrict__ slot_edge, const int* __restrict__ slot_active,
                                   float* __restrict__ out, int n_slots, int beam, int max_edges, int D) {
+  pdl_wait();
   const int d4 = D >> 2;
   const long long total = (long long)n_slots * d4;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -44,6 +45,7 @@ __global__ void kv_append_kernel(const float* __restrict__ k_new, const float* _
                                  float* __restrict__ kcache, float* __restrict__ vcache,
                                  const int* __restrict__ slot_edge, const int* __restrict__ slot_active, int n_slots,
                                  int beam, int max_edges, int HD) {
+  pdl_wait();
   const int d4 = HD >> 2;
   const long long total = (long long)n_slots * d4;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -67,6 +69,7 @@ tree_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_self, 
                  const float* __restrict__ kcache, const float* __restrict__ vcache, const int* __restrict__ edge_prev,
                  const int* __restrict__ slot_edge, const int* __restrict__ slot_active, float* __restrict__ out,
                  int n_slots, int beam, int max_edges, int H, int window, float scale) {
+  pdl_wait();
   constexpr int R = D / 32 > 0 ? D / 32 : 1;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n_slots * H) return;
@@ -120,6 +123,7 @@ beam_advance_kernel(const pka_beam_desc d, const float* __restrict__ logits, int
                     int* __restrict__ n_edges, int* __restrict__ beam_edges, int* __restrict__ beam_count,
                     int* __restrict__ slot_edge, int* __restrict__ slot_active, int* __restrict__ curr_length,
                     int* __restrict__ done, int* __restrict__ n_not_done) {
+  pdl_wait();
   extern __shared__ double cand[];                       // [beam*V + beam]
   __shared__ float lse_s[64];
   __shared__ double wbest[4];
@@ -238,7 +242,7 @@ extern "C" int pka_beam_embed(const float* emb, const float* pos, const int32_t*
   const long long total = (long long)n_utt * beam * (D / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  beam_embed_kernel<<<blocks, 256, 0, as_stream(stream)>>>(emb, pos, edge_word, edge_depth, slot_edge, slot_active, out, n_utt * beam, beam, max_edges, D);
+  launch_k(beam_embed_kernel, blocks, 256, 0, as_stream(stream), emb, pos, edge_word, edge_depth, slot_edge, slot_active, out, n_utt * beam, beam, max_edges, D);
   return check_launch("beam_embed");
 }
 
@@ -250,7 +254,7 @@ extern "C" int pka_kv_append(const float* k_new, const float* v_new, int ld, flo
   const long long total = (long long)n_utt * beam * (HD / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  kv_append_kernel<<<blocks, 256, 0, as_stream(stream)>>>(k_new, v_new, ld, kcache, vcache, slot_edge, slot_active, n_utt * beam, beam, max_edges, HD);
+  launch_k(kv_append_kernel, blocks, 256, 0, as_stream(stream), k_new, v_new, ld, kcache, vcache, slot_edge, slot_active, n_utt * beam, beam, max_edges, HD);
   return check_launch("kv_append");
 }
 
@@ -265,7 +269,7 @@ extern "C" int pka_tree_attn(const float* q, const float* k_self, const float* v
   const int warps = n_slots * H;
   const int blocks = (warps + 3) / 4;
   cudaStream_t st = as_stream(stream);
-#define TREE(DD) tree_attn_kernel<DD><<<blocks, 128, 0, st>>>(q, k_self, v_self, ld, kcache, vcache, edge_prev, slot_edge, slot_active, out, n_slots, beam, max_edges, H, window, scale)
+#define TREE(DD) launch_k(tree_attn_kernel<DD>, blocks, 128, 0, st, q, k_self, v_self, ld, kcache, vcache, edge_prev, slot_edge, slot_active, out, n_slots, beam, max_edges, H, window, scale)
   if (dk == 16) TREE(16); else if (dk == 32) TREE(32); else if (dk == 64) TREE(64); else TREE(128);
 #undef TREE
   return check_launch("tree_attn");
@@ -285,6 +289,6 @@ extern "C" int pka_beam_advance(const pka_beam_desc* d, const float* logits, int
     cudaError_t e = cudaFuncSetAttribute(beam_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "beam_advance: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
   }
-  beam_advance_kernel<<<d->n_utt, 128, smem, as_stream(stream)>>>(*d, logits, edge_prev, edge_word, edge_depth, edge_weight, n_edges, beam_edges, beam_count, slot_edge, slot_active, curr_length, done, n_not_done);
+  launch_k(beam_advance_kernel, d->n_utt, 128, smem, as_stream(stream), *d, logits, edge_prev, edge_word, edge_depth, edge_weight, n_edges, beam_edges, beam_count, slot_edge, slot_active, curr_length, done, n_not_done);
   return check_launch("beam_advance");
 }

@@ -2,6 +2,7 @@
 // All kernels use 128-bit accesses where the shape allows, grid-stride loops sized in multiples of the SM count.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace pka {
 
@@ -25,6 +26,12 @@ int check_launch(const char* what) {
   return PKA_OK;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PKA_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
 static inline int grid_for(long long work_items, int per_block) {
   long long b = (work_items + per_block - 1) / per_block;
   long long cap = (long long)kNumSMs * 16;
@@ -38,6 +45,7 @@ template <typename T>
 __global__ void embed_pos_fwd_kernel(const long long* __restrict__ tok, const float* __restrict__ emb,
                                      const float* __restrict__ pos, T* __restrict__ out, int B, int L, int D, int V,
                                      const pka_dropout drop) {
+  pdl_wait();
   DropCtx dc = make_drop(drop);
   const int d4 = D >> 2;
   const long long total = (long long)B * L * d4;
@@ -66,6 +74,7 @@ template <typename T>
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, const T* __restrict__ dout,
                                  float* __restrict__ demb, long long n_tok, int D, int padding_idx,
                                  const pka_dropout drop) {
+  pdl_wait();
   __shared__ int match[kEmbChunk];
   __shared__ int n_match;
   const int v = blockIdx.x;
@@ -110,6 +119,7 @@ template <typename T>
 __global__ void add_rowvec_dropout_kernel(const T* __restrict__ x, const float* __restrict__ rowvec,
                                           T* __restrict__ out, long long rows, int D, int period,
                                           const pka_dropout drop) {
+  pdl_wait();
   DropCtx dc = make_drop(drop);
   const int d4 = D >> 2;
   const long long total = rows * d4;
@@ -131,6 +141,7 @@ __global__ void add_rowvec_dropout_kernel(const T* __restrict__ x, const float* 
 
 template <typename T>
 __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long long n4, const pka_dropout drop) {
+  pdl_wait();
   DropCtx dc = make_drop(drop);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
     float4 g = ld4(dy + e * 4);
@@ -145,6 +156,7 @@ __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx,
 template <typename T>
 __global__ void relu_drop_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz,
                                      long long n4, float scale) {
+  pdl_wait();
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
     const float4 g = ld4(dy + e * 4), yv = ld4(y + e * 4);
     float4 o;
@@ -157,6 +169,7 @@ __global__ void relu_drop_bwd_kernel(const T* __restrict__ dy, const T* __restri
 }
 
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, const pka_dropout drop) {
+  pdl_wait();
   DropCtx dc = make_drop(drop);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     keep[e] = (dc.p > 0.f) ? (dropout_keep(dc, (unsigned long long)e) ? 1 : 0) : 1;
@@ -166,6 +179,7 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, con
 constexpr int kColsumRowsPerChunk = 64;
 template <typename T>
 __global__ void colsum_part_kernel(const T* __restrict__ x, float* __restrict__ part, long long rows, int N, int ld) {
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const long long r0 = (long long)blockIdx.y * kColsumRowsPerChunk;
@@ -187,6 +201,7 @@ constexpr int kColsumVecRows = 128;
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_part4_kernel(const T* __restrict__ x, float* __restrict__ part, long long rows, int N, int ld) {
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 128 + tx * 4;
@@ -218,6 +233,7 @@ colsum_part4_kernel(const T* __restrict__ x, float* __restrict__ part, long long
 // partial matrix), fixed-order combine through shared memory
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int chunks, int N, int accumulate) {
+  pdl_wait();
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
@@ -243,11 +259,13 @@ colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, in
 // ---------------------------------------------------------------------------------------------- cast / transpose
 template <typename S, typename Dt>
 __global__ void cast_kernel(const S* __restrict__ s, Dt* __restrict__ d, long long n) {
+  pdl_wait();
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     d[e] = from_f<Dt>(to_f(s[e]));
 }
 template <typename S, typename Dt>
 __global__ void transpose_kernel(const S* __restrict__ s, Dt* __restrict__ d, int rows, int cols) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -267,6 +285,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             float* __restrict__ v, long long n, const float* __restrict__ lr_dev, float lr_host,
             const long long* __restrict__ state, float b1, float b2, float eps,
             __nv_bfloat16* __restrict__ shadow) {
+  pdl_wait();
   __shared__ float s_step, s_isb2;
   if (threadIdx.x == 0) {
     // bias corrections in double, once per CTA (torch computes them on the host in double precision)
@@ -300,12 +319,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     if (shadow) shadow[e] = __float2bfloat16_rn(pv);
   }
 }
-__global__ void adam_t_inc_kernel(long long* state) { state[0] += 1; }
+__global__ void adam_t_inc_kernel(long long* state) {
+  pdl_wait(); state[0] += 1; }
 __global__ void lr_tick_kernel(float* lr, long long* state, float start_lr, float c) {
+  pdl_wait();
   state[1] += 1;
   lr[0] = (start_lr * c) / ((float)state[1] + c);
 }
-__global__ void counter_inc_kernel(unsigned long long* c) { c[0] += 1ull; }
+__global__ void counter_inc_kernel(unsigned long long* c) {
+  pdl_wait(); c[0] += 1ull; }
 
 }  // namespace pka
 
@@ -336,7 +358,7 @@ extern "C" int pka_embed_pos_fwd(const int64_t* tok, const float* emb, const flo
   PKA_REQUIRE(B > 0 && L > 0 && D > 0 && D % 4 == 0, PKA_EUNSUPPORTED, "embed_pos_fwd: B=%d L=%d D=%d (D%%4)", B, L, D);
   pka_dropout dr = drop ? *drop : no_dropout();
   const long long total = (long long)B * L * (D / 4);
-  DISPATCH_T(dtype, "embed_pos_fwd", (embed_pos_fwd_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const long long*)tok, emb, pos, (T*)out, B, L, D, V, dr)));
+  DISPATCH_T(dtype, "embed_pos_fwd", (launch_k(embed_pos_fwd_kernel<T>, grid_for(total, 256), 256, 0, as_stream(stream), (const long long*)tok, emb, pos, (T*)out, B, L, D, V, dr)));
   return check_launch("embed_pos_fwd");
 }
 
@@ -346,7 +368,7 @@ extern "C" int pka_embed_bwd(const int64_t* tok, const void* dout, float* demb, 
   PKA_REQUIRE(B > 0 && L > 0 && D > 0 && V > 0, PKA_EINVAL, "embed_bwd: bad sizes");
   pka_dropout dr = drop ? *drop : no_dropout();
   const int threads = D >= 256 ? 256 : (D >= 128 ? 128 : 64);
-  DISPATCH_T(dtype, "embed_bwd", (embed_bwd_kernel<T><<<V, threads, 0, as_stream(stream)>>>((const long long*)tok, (const T*)dout, demb, (long long)B * L, D, padding_idx, dr)));
+  DISPATCH_T(dtype, "embed_bwd", (launch_k(embed_bwd_kernel<T>, V, threads, 0, as_stream(stream), (const long long*)tok, (const T*)dout, demb, (long long)B * L, D, padding_idx, dr)));
   return check_launch("embed_bwd");
 }
 
@@ -356,7 +378,7 @@ extern "C" int pka_add_rowvec_dropout_fwd(const void* x, const float* rowvec, vo
   PKA_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && (!rowvec || period > 0), PKA_EUNSUPPORTED, "add_rowvec_dropout_fwd: rows=%lld D=%d", (long long)rows, D);
   pka_dropout dr = drop ? *drop : no_dropout();
   const long long total = rows * (D / 4);
-  DISPATCH_T(dtype, "add_rowvec_dropout_fwd", (add_rowvec_dropout_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, rowvec, (T*)out, rows, D, period, dr)));
+  DISPATCH_T(dtype, "add_rowvec_dropout_fwd", (launch_k(add_rowvec_dropout_kernel<T>, grid_for(total, 256), 256, 0, as_stream(stream), (const T*)x, rowvec, (T*)out, rows, D, period, dr)));
   return check_launch("add_rowvec_dropout_fwd");
 }
 
@@ -364,14 +386,14 @@ extern "C" int pka_dropout_bwd(const void* dy, void* dx, int dtype, int64_t n, c
   PKA_REQUIRE(dy && dx, PKA_EINVAL, "dropout_bwd: null pointer");
   PKA_REQUIRE(n > 0 && n % 4 == 0, PKA_EUNSUPPORTED, "dropout_bwd: n=%lld must be a positive multiple of 4", (long long)n);
   pka_dropout dr = drop ? *drop : no_dropout();
-  DISPATCH_T(dtype, "dropout_bwd", (dropout_bwd_kernel<T><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (T*)dx, n / 4, dr)));
+  DISPATCH_T(dtype, "dropout_bwd", (launch_k(dropout_bwd_kernel<T>, grid_for(n / 4, 256), 256, 0, as_stream(stream), (const T*)dy, (T*)dx, n / 4, dr)));
   return check_launch("dropout_bwd");
 }
 
 extern "C" int pka_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float scale, void* stream) {
   PKA_REQUIRE(dy && y && dz, PKA_EINVAL, "relu_drop_bwd: null pointer");
   PKA_REQUIRE(n > 0 && n % 4 == 0, PKA_EUNSUPPORTED, "relu_drop_bwd: n=%lld must be a positive multiple of 4", (long long)n);
-  DISPATCH_T(dtype, "relu_drop_bwd", (relu_drop_bwd_kernel<T><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dz, n / 4, scale)));
+  DISPATCH_T(dtype, "relu_drop_bwd", (launch_k(relu_drop_bwd_kernel<T>, grid_for(n / 4, 256), 256, 0, as_stream(stream), (const T*)dy, (const T*)y, (T*)dz, n / 4, scale)));
   return check_launch("relu_drop_bwd");
 }
 
@@ -388,20 +410,20 @@ extern "C" int pka_colsum(const void* x, float* out, float* part_ws, int dtype, 
   if (vec) {
     chunks = (int)((rows + kColsumVecRows - 1) / kColsumVecRows);        // never more than the workspace was sized for
     dim3 grid((N + 127) / 128, chunks);
-    DISPATCH_T(dtype, "colsum", (colsum_part4_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, part_ws, rows, N, ld)));
+    DISPATCH_T(dtype, "colsum", (launch_k(colsum_part4_kernel<T>, grid, 256, 0, as_stream(stream), (const T*)x, part_ws, rows, N, ld)));
   } else {
     dim3 grid((N + 127) / 128, chunks);
-    DISPATCH_T(dtype, "colsum", (colsum_part_kernel<T><<<grid, 128, 0, as_stream(stream)>>>((const T*)x, part_ws, rows, N, ld)));
+    DISPATCH_T(dtype, "colsum", (launch_k(colsum_part_kernel<T>, grid, 128, 0, as_stream(stream), (const T*)x, part_ws, rows, N, ld)));
   }
   int rc = check_launch("colsum_part");
   if (rc) return rc;
-  colsum_finish_kernel<<<(N + 31) / 32, 256, 0, as_stream(stream)>>>(part_ws, out, chunks, N, accumulate);
+  launch_k(colsum_finish_kernel, (N + 31) / 32, 256, 0, as_stream(stream), part_ws, out, chunks, N, accumulate);
   return check_launch("colsum_finish");
 }
 
 extern "C" int pka_dropout_mask(uint8_t* keep, int64_t n, const pka_dropout* drop, void* stream) {
   PKA_REQUIRE(keep && drop && n > 0, PKA_EINVAL, "dropout_mask: bad arguments");
-  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(keep, n, *drop);
+  launch_k(dropout_mask_kernel, grid_for(n, 256), 256, 0, as_stream(stream), keep, n, *drop);
   return check_launch("dropout_mask");
 }
 
@@ -409,10 +431,10 @@ extern "C" int pka_cast(const void* src, int sd, void* dst, int dd, int64_t n, v
   PKA_REQUIRE(src && dst && n > 0, PKA_EINVAL, "cast: bad arguments");
   cudaStream_t st = as_stream(stream);
   const int g = grid_for(n, 256);
-  if (sd == PKA_F32 && dd == PKA_BF16) cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
-  else if (sd == PKA_BF16 && dd == PKA_F32) cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
-  else if (sd == PKA_F32 && dd == PKA_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
-  else if (sd == PKA_BF16 && dd == PKA_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  if (sd == PKA_F32 && dd == PKA_BF16) launch_k(cast_kernel<float, __nv_bfloat16>, g, 256, 0, st, (const float*)src, (__nv_bfloat16*)dst, n);
+  else if (sd == PKA_BF16 && dd == PKA_F32) launch_k(cast_kernel<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, (float*)dst, n);
+  else if (sd == PKA_F32 && dd == PKA_F32) launch_k(cast_kernel<float, float>, g, 256, 0, st, (const float*)src, (float*)dst, n);
+  else if (sd == PKA_BF16 && dd == PKA_BF16) launch_k(cast_kernel<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "cast: dtypes %d -> %d", sd, dd);
   return check_launch("cast");
 }
@@ -422,10 +444,10 @@ extern "C" int pka_transpose(const void* src, int sd, void* dst, int dd, int row
   cudaStream_t st = as_stream(stream);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   PKA_REQUIRE(grid.y <= 65535, PKA_EUNSUPPORTED, "transpose: too many rows");
-  if (sd == PKA_F32 && dd == PKA_BF16) transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, rows, cols);
-  else if (sd == PKA_BF16 && dd == PKA_F32) transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, rows, cols);
-  else if (sd == PKA_F32 && dd == PKA_F32) transpose_kernel<float, float><<<grid, block, 0, st>>>((const float*)src, (float*)dst, rows, cols);
-  else if (sd == PKA_BF16 && dd == PKA_BF16) transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols);
+  if (sd == PKA_F32 && dd == PKA_BF16) launch_k(transpose_kernel<float, __nv_bfloat16>, grid, block, 0, st, (const float*)src, (__nv_bfloat16*)dst, rows, cols);
+  else if (sd == PKA_BF16 && dd == PKA_F32) launch_k(transpose_kernel<__nv_bfloat16, float>, grid, block, 0, st, (const __nv_bfloat16*)src, (float*)dst, rows, cols);
+  else if (sd == PKA_F32 && dd == PKA_F32) launch_k(transpose_kernel<float, float>, grid, block, 0, st, (const float*)src, (float*)dst, rows, cols);
+  else if (sd == PKA_BF16 && dd == PKA_BF16) launch_k(transpose_kernel<__nv_bfloat16, __nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "transpose: dtypes %d -> %d", sd, dd);
   return check_launch("transpose");
 }
@@ -436,21 +458,21 @@ extern "C" int pka_adam_step(float* param, const float* grad, float* exp_avg, fl
   PKA_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, PKA_EINVAL, "adam_step: bad arguments");
   cudaStream_t st = as_stream(stream);
   PKA_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), PKA_EALIGN, "adam_step: the arenas must be 16-byte aligned");
-  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
+  launch_k(adam_kernel, grid_for((n + 3) / 4, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
   int rc = check_launch("adam");
   if (rc) return rc;
-  adam_t_inc_kernel<<<1, 1, 0, st>>>((long long*)state);
+  launch_k(adam_t_inc_kernel, 1, 1, 0, st, (long long*)state);
   return check_launch("adam_t_inc");
 }
 
 extern "C" int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream) {
   PKA_REQUIRE(lr_dev && state, PKA_EINVAL, "lr_tick: null pointer");
-  lr_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(lr_dev, (long long*)state, start_lr, soft_coefficient);
+  launch_k(lr_tick_kernel, 1, 1, 0, as_stream(stream), lr_dev, (long long*)state, start_lr, soft_coefficient);
   return check_launch("lr_tick");
 }
 
 extern "C" int pka_counter_inc(uint64_t* counter, void* stream) {
   PKA_REQUIRE(counter, PKA_EINVAL, "counter_inc: null pointer");
-  counter_inc_kernel<<<1, 1, 0, as_stream(stream)>>>((unsigned long long*)counter);
+  launch_k(counter_inc_kernel, 1, 1, 0, as_stream(stream), (unsigned long long*)counter);
   return check_launch("counter_inc");
 }

@@ -16,6 +16,7 @@ namespace pka {
 __global__ void __launch_bounds__(256)
 cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths, float* __restrict__ stats, int T, int F,
                   int norm_vars) {
+  pdl_wait();
   extern __shared__ double sm[];                  // [256][8]: 4 sums + 4 sums of squares per thread
   const int b = blockIdx.x, tid = threadIdx.x;
   int n = lengths[b];
@@ -81,6 +82,7 @@ template <typename To, int VEC>
 __global__ void __launch_bounds__(256)
 frontend_kernel(const FrontP p, const float* __restrict__ x, const int* __restrict__ lengths,
                 const float* __restrict__ stats, To* __restrict__ out) {
+  pdl_wait();
   __shared__ short g_shift[kFeMaxGroups], g_fr[kFeMaxGroups], g_f[kFeMaxGroups];
   const int Tf = p.T / p.fold, Ff = p.F * p.fold, W = p.n_ctx * Ff;
   const unsigned G = (unsigned)(W / VEC);
@@ -149,7 +151,7 @@ extern "C" int pka_frontend_fwd(const float* feats, const int32_t* lengths, void
   PKA_REQUIRE(cmvn_mode == 0 || (lengths && stats_ws), PKA_EINVAL, "frontend_fwd: CMVN needs lengths and stats_ws");
   cudaStream_t st = as_stream(stream);
   if (cmvn_mode) {
-    cmvn_stats_kernel<<<B, 256, 256 * 8 * sizeof(double), st>>>(feats, lengths, stats_ws, T, F, cmvn_mode == 2);
+    launch_k(cmvn_stats_kernel, B, 256, 256 * 8 * sizeof(double), st, feats, lengths, stats_ws, T, F, cmvn_mode == 2);
     int rc = check_launch("cmvn_stats");
     if (rc) return rc;
   }
@@ -164,7 +166,7 @@ extern "C" int pka_frontend_fwd(const float* feats, const int32_t* lengths, void
   if (blocks < 1) blocks = 1;
   const bool v4 = (F % 4 == 0) && aligned16(feats) && aligned16(out);
   const bool v8 = v4 && (F % 8 == 0);
-#define PKA_FE(To, V) frontend_kernel<To, V><<<(int)blocks, 256, 0, st>>>(p, feats, lengths, stats_ws, (To*)out)
+#define PKA_FE(To, V) launch_k(frontend_kernel<To, V>, (int)blocks, 256, 0, st, p, feats, lengths, stats_ws, (To*)out)
   if (out_dtype == PKA_F32) {
     if (v4) PKA_FE(float, 4); else PKA_FE(float, 1);
   } else if (out_dtype == PKA_BF16) {

@@ -29,6 +29,7 @@ struct GemmParams {
 template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_f32_kernel(const GemmParams p) {
+  pdl_wait();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
   static_assert(TM % 4 == 0 && TN % 4 == 0, "micro-tile is built from float4 groups");
@@ -204,6 +205,7 @@ gemm_f32_kernel(const GemmParams p) {
 }
 
 __global__ void splitk_reduce_kernel(const GemmParams p) {
+  pdl_wait();
   const long long per = (long long)p.M * p.N, total = per * p.nbatch;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int batch = (int)(e / per);
@@ -220,10 +222,10 @@ template <int BM, int BN, int TM, int TN>
 static int launch_cfg(const GemmParams& p, int transA, int transB, int nbatch, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nbatch * p.splitk);
   dim3 block((BM / TM) * (BN / TN));
-  if (!transA && transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, true><<<grid, block, 0, st>>>(p);
-  else if (!transA && !transB) gemm_f32_kernel<BM, BN, 32, TM, TN, false, false><<<grid, block, 0, st>>>(p);
-  else if (transA && !transB) gemm_f32_kernel<BM, BN, 32, TM, TN, true, false><<<grid, block, 0, st>>>(p);
-  else gemm_f32_kernel<BM, BN, 32, TM, TN, true, true><<<grid, block, 0, st>>>(p);
+  if (!transA && transB) launch_k(gemm_f32_kernel<BM, BN, 32, TM, TN, false, true>, grid, block, 0, st, p);
+  else if (!transA && !transB) launch_k(gemm_f32_kernel<BM, BN, 32, TM, TN, false, false>, grid, block, 0, st, p);
+  else if (transA && !transB) launch_k(gemm_f32_kernel<BM, BN, 32, TM, TN, true, false>, grid, block, 0, st, p);
+  else launch_k(gemm_f32_kernel<BM, BN, 32, TM, TN, true, true>, grid, block, 0, st, p);
   return check_launch("gemm_f32");
 }
 
@@ -264,6 +266,6 @@ extern "C" int pka_gemm_f32(const pka_gemm_desc* d, void* stream) {
   if (rc || p.splitk == 1) return rc;
   long long total = (long long)p.M * p.N * p.nbatch;
   int blocks = (int)((total + 255) / 256 < (long long)kNumSMs * 8 ? (total + 255) / 256 : (long long)kNumSMs * 8);
-  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+  launch_k(splitk_reduce_kernel, blocks, 256, 0, st, p);
   return check_launch("gemm_f32 split-K reduce");
 }

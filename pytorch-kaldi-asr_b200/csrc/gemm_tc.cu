@@ -87,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // the prologue above touched only shared / tensor memory
 
   if (warp == 0) {
     if (lane == 0) {                               // ===== TMA producer
@@ -249,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 // fixed-order sum of the split partials: out[m, n] (+)= sum_s ws[s][m][n]
 __global__ void tc_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long per, int splits, int accumulate) {
+  pdl_wait();
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < per; e += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int sp = 0; sp < splits; ++sp) s += ws[(long long)sp * per + e];
@@ -260,6 +262,7 @@ __global__ void tc_reduce_kernel(const float* __restrict__ ws, float* __restrict
 // (the data-gradient operand: K-major in the output-channel index)
 __global__ void weight_relayout_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wf,
                                        __nv_bfloat16* __restrict__ Wd, int N, int K, int nseg) {
+  pdl_wait();
   const long long total = (long long)N * nseg * K;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int o = (int)(e / ((long long)nseg * K));
@@ -276,6 +279,7 @@ __global__ void weight_relayout_kernel(const float* __restrict__ W, __nv_bfloat1
 struct HeadPtrs { const float* w[3]; float* g[3]; };
 __global__ void head_weight_relayout_kernel(HeadPtrs hp, __nv_bfloat16* __restrict__ Wf, __nv_bfloat16* __restrict__ Wd,
                                             int P, int H, int D, int dk) {
+  pdl_wait();
   const long long per = (long long)H * D * dk, total = per * P;
   const int ntot = P * H * dk;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -290,6 +294,7 @@ __global__ void head_weight_relayout_kernel(HeadPtrs hp, __nv_bfloat16* __restri
 }
 // dWcat fp32 [(p,h,j), d] -> dw_p[h, d, j]
 __global__ void head_grad_relayout_kernel(HeadPtrs hp, const float* __restrict__ dWcat, int P, int H, int D, int dk) {
+  pdl_wait();
   const long long per = (long long)H * D * dk, total = per * P;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int pidx = (int)(e / per);
@@ -304,6 +309,7 @@ template <typename Tin>
 __global__ void relu_bwd_dual_kernel(const Tin* __restrict__ dY, const __nv_bfloat16* __restrict__ Y,
                                      __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZt, int Bt, int T, int Tp,
                                      int N, float scale, int gate) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -439,7 +445,7 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
     p.tb_per_utt = (d->T + TC_BK - 1) / TC_BK;
     grid = dim3((d->M + TC_BM - 1) / TC_BM, ((d->N + TC_BN - 1) / TC_BN) * d->nseg, d->splits);
   }
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(mapA, mapB, p);
+  launch_k(gemm_tc_kernel, grid, TC_THREADS, TC_SMEM, as_stream(stream), mapA, mapB, p);
   return check_launch("gemm_tc");
 }
 
@@ -447,7 +453,7 @@ extern "C" int pka_tc_reduce(const float* ws, float* out, int64_t per, int split
   PKA_REQUIRE(ws && out && per > 0 && splits >= 1, PKA_EINVAL, "tc_reduce: bad arguments");
   long long blocks = (per + 255) / 256;
   if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-  tc_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(ws, out, per, splits, accumulate);
+  launch_k(tc_reduce_kernel, (int)blocks, 256, 0, as_stream(stream), ws, out, per, splits, accumulate);
   return check_launch("tc_reduce");
 }
 
@@ -456,7 +462,7 @@ extern "C" int pka_weight_relayout(const float* W, void* Wf, void* Wd, int N, in
   const long long total = (long long)N * nseg * K;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-  weight_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(W, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, N, K, nseg);
+  launch_k(weight_relayout_kernel, (int)blocks, 256, 0, as_stream(stream), W, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, N, K, nseg);
   return check_launch("weight_relayout");
 }
 
@@ -466,9 +472,9 @@ extern "C" int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, vo
   PKA_REQUIRE(Bt > 0 && Bt <= 65535 && T > 0 && N > 0 && Tp >= T, PKA_EINVAL, "relu_bwd_dual: bad sizes");
   dim3 grid((N + 31) / 32, (T + 31) / 32, Bt), block(32, 8);
   if (dy_dtype == PKA_BF16)
-    relu_bwd_dual_kernel<__nv_bfloat16><<<grid, block, 0, as_stream(stream)>>>((const __nv_bfloat16*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
+    launch_k(relu_bwd_dual_kernel<__nv_bfloat16>, grid, block, 0, as_stream(stream), (const __nv_bfloat16*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
   else if (dy_dtype == PKA_F32)
-    relu_bwd_dual_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
+    launch_k(relu_bwd_dual_kernel<float>, grid, block, 0, as_stream(stream), (const float*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, (__nv_bfloat16*)dZt, Bt, T, Tp, N, scale, gate);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "relu_bwd_dual: dtype %d", dy_dtype);
   return check_launch("relu_bwd_dual");
 }
@@ -480,7 +486,7 @@ extern "C" int pka_head_weight_relayout(const float* w0, const float* w1, const 
   const long long total = (long long)P * H * D * dk;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-  head_weight_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(hp, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, P, H, D, dk);
+  launch_k(head_weight_relayout_kernel, (int)blocks, 256, 0, as_stream(stream), hp, (__nv_bfloat16*)Wf, (__nv_bfloat16*)Wd, P, H, D, dk);
   return check_launch("head_weight_relayout");
 }
 
@@ -491,6 +497,6 @@ extern "C" int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, 
   const long long total = (long long)P * H * D * dk;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
-  head_grad_relayout_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(hp, dWcat, P, H, D, dk);
+  launch_k(head_grad_relayout_kernel, (int)blocks, 256, 0, as_stream(stream), hp, dWcat, P, H, D, dk);
   return check_launch("head_grad_relayout");
 }

@@ -146,6 +146,9 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   if (csize > 1) cluster_sync_relaxed();           // every CTA's barriers exist (fence.mbarrier_init above) before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster hand-shake) may overlap the
+  // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.
+  pdl_wait();
   if (threadIdx.x == 0) stamp(p.dbg, 1);
 
   if (warp == 0 || warp == 10) {
@@ -497,10 +500,13 @@ int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled) {
   cfg.blockDim = dim3(R2_THREADS, 1, 1);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pl.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (pdl_enabled()) cfg.numAttrs = 2;
   cudaError_t e = pl.pair ? cudaLaunchKernelEx(&cfg, gemm_tc_rows2_kernel<true>, mapA, mapB, mapC, p)
                           : cudaLaunchKernelEx(&cfg, gemm_tc_rows2_kernel<false>, mapA, mapB, mapC, p);
   PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_tc rows2 launch failed: %s", cudaGetErrorString(e));

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ a,
                   const float* __restrict__ bta, T* __restrict__ y, float* __restrict__ mean_o,
                   float* __restrict__ rinv_o, int rows, int D, float eps, const pka_dropout drop) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
   if (row >= rows) return;
@@ -128,6 +129,7 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
                   const float* __restrict__ a, const float* __restrict__ mean_i, const float* __restrict__ rinv_i,
                   T* __restrict__ dx, T* __restrict__ dres, float* __restrict__ dab_ws, int rows, int D, float eps,
                   const pka_dropout drop) {
+  pdl_wait();
   __shared__ float red[kLnWarps][2][32 * EV * VPL];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DropCtx dc = make_drop(drop);
@@ -223,6 +225,7 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
 // take interleaved partial rows (coalesced 128 B reads), fixed-order combine through shared memory (deterministic)
 __global__ void __launch_bounds__(256)
 ln_dab_finish_kernel(const float* __restrict__ ws, float* __restrict__ da, float* __restrict__ db, int nblk, int D) {
+  pdl_wait();
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cols32 = (D + 31) / 32;
@@ -250,7 +253,7 @@ template <typename T>
 static int fwd_t(const void* x, const void* res, const float* a, const float* b, void* y, float* mean, float* rinv,
                  int rows, int D, float eps, const pka_dropout& dr, cudaStream_t st) {
   dim3 grid((rows + kLnWarps - 1) / kLnWarps), block(kLnWarps * 32);
-#define LN_FWD(E, V) add_ln_fwd_kernel<T, E, V><<<grid, block, 0, st>>>((const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
+#define LN_FWD(E, V) launch_k(add_ln_fwd_kernel<T, E, V>, grid, block, 0, st, (const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
   if (sizeof(T) == 2 && D % 8 == 0) {             // bf16: 8 elements (16 bytes) per lane and vector
     constexpr int E = sizeof(T) == 2 ? 8 : 4;
     const int vpl = (D + 255) / 256;
@@ -269,7 +272,7 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
                  const pka_dropout& dr, cudaStream_t st) {
   const int nblk = pka_ln_bwd_blocks(rows);
   dim3 grid(nblk), block(kLnWarps * 32);
-#define LN_BWD(E, V) add_ln_bwd_kernel<T, E, V><<<grid, block, 0, st>>>((const T*)dy, (const T*)x, (const T*)res, a, mean, rinv, (T*)dx, (T*)dres, ws, rows, D, eps, dr)
+#define LN_BWD(E, V) launch_k(add_ln_bwd_kernel<T, E, V>, grid, block, 0, st, (const T*)dy, (const T*)x, (const T*)res, a, mean, rinv, (T*)dx, (T*)dres, ws, rows, D, eps, dr)
   if (sizeof(T) == 2 && D % 8 == 0) {
     constexpr int E = sizeof(T) == 2 ? 8 : 4;
     const int vpl = (D + 255) / 256;
@@ -281,7 +284,7 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
 #undef LN_BWD
   int rc = check_launch("add_layernorm_bwd");
   if (rc) return rc;
-  ln_dab_finish_kernel<<<2 * ((D + 31) / 32), 256, 0, st>>>(ws, da, db, nblk, D);
+  launch_k(ln_dab_finish_kernel, 2 * ((D + 31) / 32), 256, 0, st, ws, da, db, nblk, D);
   return check_launch("ln_dab_finish");
 }
 

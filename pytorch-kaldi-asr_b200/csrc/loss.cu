@@ -15,6 +15,7 @@ template <typename T>
 __global__ void __launch_bounds__(kCeWarps * 32)
 ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal, int N, int V, int smoothing,
               float eps, float* __restrict__ lse_o, float* __restrict__ part) {
+  pdl_wait();
   __shared__ float red[kCeWarps][3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float loss = 0.f, correct = 0.f, words = 0.f;
@@ -67,6 +68,7 @@ ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal, 
 }
 
 __global__ void ce_finish_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out3) {
+  pdl_wait();
   // three lanes, each sums one statistic over the CTAs in index order (fixed order => run-to-run identical)
   if (threadIdx.x < 3) {
     float s = 0.f;
@@ -79,6 +81,7 @@ template <typename T>
 __global__ void ce_bwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal,
                               const float* __restrict__ lse, const float* __restrict__ grad_out, T* __restrict__ dl,
                               int N, int V, int smoothing, float eps) {
+  pdl_wait();
   const float go = grad_out ? grad_out[0] : 1.f;
   const float off = smoothing ? eps / (float)(V - 1) : 0.f;
   const float on = smoothing ? 1.f - eps : 1.f;
@@ -112,13 +115,13 @@ extern "C" int pka_ce_fwd(const void* logits, const int64_t* goal, int dtype, in
   const int nblk = pka_ce_blocks(N);
   cudaStream_t st = as_stream(stream);
   if (dtype == PKA_F32)
-    ce_fwd_kernel<float><<<nblk, kCeWarps * 32, 0, st>>>((const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+    launch_k(ce_fwd_kernel<float>, nblk, kCeWarps * 32, 0, st, (const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
   else if (dtype == PKA_BF16)
-    ce_fwd_kernel<__nv_bfloat16><<<nblk, kCeWarps * 32, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+    launch_k(ce_fwd_kernel<__nv_bfloat16>, nblk, kCeWarps * 32, 0, st, (const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_fwd: dtype %d", dtype);
   int rc = check_launch("ce_fwd");
   if (rc) return rc;
-  ce_finish_kernel<<<1, 32, 0, st>>>(part_ws, nblk, out3);
+  launch_k(ce_finish_kernel, 1, 32, 0, st, part_ws, nblk, out3);
   return check_launch("ce_finish");
 }
 
@@ -132,9 +135,9 @@ extern "C" int pka_ce_bwd(const void* logits, const int64_t* goal, const float* 
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   cudaStream_t st = as_stream(stream);
   if (dtype == PKA_F32)
-    ce_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)logits, (const long long*)goal, lse, grad_out, (float*)dlogits, N, V, smoothing, eps);
+    launch_k(ce_bwd_kernel<float>, blocks, 256, 0, st, (const float*)logits, (const long long*)goal, lse, grad_out, (float*)dlogits, N, V, smoothing, eps);
   else if (dtype == PKA_BF16)
-    ce_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)goal, lse, grad_out, (__nv_bfloat16*)dlogits, N, V, smoothing, eps);
+    launch_k(ce_bwd_kernel<__nv_bfloat16>, blocks, 256, 0, st, (const __nv_bfloat16*)logits, (const long long*)goal, lse, grad_out, (__nv_bfloat16*)dlogits, N, V, smoothing, eps);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_bwd: dtype %d", dtype);
   return check_launch("ce_bwd");
 }

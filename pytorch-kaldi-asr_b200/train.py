@@ -38,15 +38,22 @@ def _to_device(batch, device, non_blocking=True):
 
 class _Prefetcher:
     """Host->device staging with one batch of look-ahead on a side stream (double buffering): `take()` hands out the
-    staged batch, `stage_next()` -- called right after the step's kernels have been launched and before any host
-    sync -- starts the H2D copies of the following batch so they overlap the running step (pinned host batches copy
-    asynchronously).  The reference copies synchronously inside the step (L/train.py:151-161)."""
+    staged batch, `release()` + `stage_next()` -- called right after the step's kernels have been launched and before
+    any host sync -- start the H2D copies of the following batch so they overlap the running step (pinned host batches
+    copy asynchronously).  Two sets of device staging buffers are reused while the batch shape stays the same, so the
+    steady state performs no allocation.  The reference copies synchronously inside the step (L/train.py:151-161)."""
+
+    _DTYPES = (torch.float32, torch.uint8, torch.int64, torch.uint8)
 
     def __init__(self, batch_loader, device):
         self.device = device
         self.copy_stream = torch.cuda.Stream(device=device)
         self.it = iter(batch_loader)
+        self.slots = [None, None]          # device staging buffers
+        self.free_ev = [None, None]        # compute-stream event: the consumer of this slot has finished reading it
+        self.n = 0
         self.staged = None
+        self.cur_slot = None
         self.stage_next()
 
     def stage_next(self):
@@ -55,22 +62,43 @@ class _Prefetcher:
         except StopIteration:
             self.staged = None
             return
+        slot = self.n % 2
+        self.n += 1
+        hosts = []
+        for x, dt in zip(batch[1:5], self._DTYPES):
+            hosts.append(x.to(dt) if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x), dtype=dt))
         with torch.cuda.stream(self.copy_stream):
-            tensors = _to_device(batch, self.device)
+            if self.free_ev[slot] is not None:
+                self.copy_stream.wait_event(self.free_ev[slot])
+            bufs = self.slots[slot]
+            if bufs is None or any(tuple(b.shape) != tuple(h.shape) for b, h in zip(bufs, hosts)):
+                bufs = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in hosts]
+                self.slots[slot] = bufs
+            for b, h in zip(bufs, hosts):
+                b.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self.staged = (tensors, ev)
+        self.staged = (tuple(bufs), ev, slot)
 
     def take(self):
         if self.staged is None:
             return None
-        tensors, ev = self.staged
+        tensors, ev, slot = self.staged
         self.staged = None
+        self.cur_slot = slot
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
         for t in tensors:
             t.record_stream(cur)
         return tensors
+
+    def release(self):
+        """Everything that reads the batch handed out by the last take() has been enqueued on the current stream."""
+        if self.cur_slot is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.free_ev[self.cur_slot] = ev
+            self.cur_slot = None
 
 
 def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_eval=10, use_gpu=False, seq_error_prob=0,
@@ -128,6 +156,7 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
         src_seq, src_pad_mask, tgt_seq, tgt_pad_mask = cur
         if graphed is not None and mode == 'train':
             out = graphed.step(src_seq, src_pad_mask, tgt_seq, tgt_pad_mask)
+            feed.release()
             feed.stage_next()
             if sync_every_step:
                 read_back(out)
@@ -148,6 +177,7 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
             loss.backward()
             optimizer.step()
             optimizer.update_learning_rate()
+        feed.release()
         feed.stage_next()
         if sync_every_step:
             read_back(torch.cat([loss.detach().reshape(1), stats.reshape(2)]))
