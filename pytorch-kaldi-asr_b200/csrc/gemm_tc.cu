@@ -346,7 +346,7 @@ EncodeTiledFn get_encode() {
 
 // 3-D bf16 tensor map, innermost dim first; box = {64, box1, box2}; 128B swizzle; OOB elements read as zero
 int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-                    uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who) {
+             uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who, bool f32) {
   // cuTensorMapEncodeTiled is a driver call and needs a current context in THIS thread.  Autograd worker threads may
   // not have one bound yet when their first call into the library is a tensor-core GEMM, so make the (statically
   // linked) runtime bind the primary context first -- with a call that is legal during stream capture.
@@ -363,9 +363,9 @@ int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_
               (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-  cuuint32_t box[3] = {64u, box1, box2};
+  cuuint32_t box[3] = {f32 ? 32u : 64u, box1, box2};              // 128 bytes along the contiguous dimension
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PKA_REQUIRE(r == CUDA_SUCCESS, PKA_EINVAL, "%s: cuTensorMapEncodeTiled failed with %d (dims %llu,%llu,%llu)", who, (int)r,
@@ -375,7 +375,10 @@ int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_
 
 }  // namespace pka
 
-namespace pka { int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled); }   // gemm_tc_rows.cu
+namespace pka {
+int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled);    // gemm_tc_rows.cu
+int launch_wgrad2(const pka_tc_desc* d, cudaStream_t st, bool* handled);   // gemm_tc_wgrad.cu
+}
 
 using namespace pka;
 
@@ -388,6 +391,11 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
     PKA_REQUIRE(d->drop.p == 0.f || d->N % 4 == 0, PKA_EUNSUPPORTED, "gemm_tc: dropout epilogue needs N%%4==0");
     bool handled = false;
     int rc2 = launch_rows2(d, as_stream(stream), &handled);
+    if (rc2 || handled) return rc2;
+  }
+  if (d->mode == 2 && d->M > 0 && d->splits >= 1) {   // CTA-pair weight-gradient kernel whenever the tile shape allows
+    bool handled = false;
+    int rc2 = launch_wgrad2(d, as_stream(stream), &handled);
     if (rc2 || handled) return rc2;
   }
   static bool attr_set = false;

@@ -101,6 +101,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode();
 // 3-D bf16 tensor map, innermost dim first; box = {64, box1, box2}; 128B swizzle; OOB elements read as zero
 int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
-             uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who);
+             uint64_t stride2_bytes, uint32_t box1, uint32_t box2, const char* who, bool f32 = false);   // f32: box = {32 fp32, ...}
 
 }  // namespace pka

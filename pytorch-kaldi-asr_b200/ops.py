@@ -702,8 +702,14 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None):
     activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
     split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic)."""
     assert dZ.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dZ.is_contiguous() and X.is_contiguous()
-    tiles = ((M + 127) // 128) * ((N + 127) // 128) * nseg
-    splits = max(1, min(Bt, 148 // max(1, tiles)))
+    if M % 256 == 0 and N % 256 == 0:          # CTA-pair kernel: 256x256 tiles on two SMs, reduction split in 128-frame units
+        tiles = 2 * (M // 256) * (N // 256) * nseg
+        units = Bt * ((T + 127) // 128)
+        splits = max(1, min(units, 148 // max(1, tiles)))
+        splits = -(-units // -(-units // splits))          # no empty splits
+    else:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128) * nseg
+        splits = max(1, min(Bt, 148 // max(1, tiles)))
     ws = torch.empty(splits, M, nseg * N, device=dZ.device, dtype=torch.float32)
     d = L.TcDesc()
     d.A, d.B, d.C, d.Ct, d.bias = dZ.data_ptr(), X.data_ptr(), ws.data_ptr(), 0, 0
