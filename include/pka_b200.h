@@ -210,6 +210,10 @@ int pka_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_
 int pka_colsum_chunks(int64_t rows);
 int pka_colsum(const void* x, float* out, float* part_ws, int dtype, int64_t rows, int N, int ld, int accumulate,
                void* stream);
+/* one pass: dZ (bf16 [rows,N]) = gate ? ((Y > 0) ? dY*scale : 0) : dY, and out[n] = sum_r dZ[r,n] (bias gradient of a
+ * [ReLU+dropout] linear layer).  part_ws float[pka_colsum_chunks(rows)*N]; deterministic.  N % 4 == 0. */
+int pka_gate_colsum(const void* dY, int dy_dtype, const void* Y, void* dZ, float* out, float* part_ws, int64_t rows, int N,
+                    float scale, int gate, void* stream);
 /* keep[i] = 1/0 for i < n : the bits every kernel above derives for (seed, site, *step_ptr) */
 int pka_dropout_mask(uint8_t* keep, int64_t n, const pka_dropout* drop, void* stream);
 int pka_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);

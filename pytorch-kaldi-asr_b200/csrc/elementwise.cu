@@ -229,6 +229,107 @@ colsum_part4_kernel(const T* __restrict__ x, float* __restrict__ part, long long
     *reinterpret_cast<float4*>(part + (long long)blockIdx.y * N + n) = t;
   }
 }
+// Fused backward of [ReLU ->] dropout + bias gradient: dZ = gate ? ((Y > 0) ? dY*scale : 0) : dY (bf16) and the column
+// sums of dZ in ONE pass over dY / Y (same [128 rows][128 columns] blocking and fixed-order reduction as above).
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+gate_colsum_kernel(const Tin* __restrict__ dY, const __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ dZ,
+                   float* __restrict__ part, long long rows, int N, float scale, int gate) {
+  pdl_wait();
+  __shared__ float4 red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + tx * 4;
+  const long long r0 = (long long)blockIdx.y * kColsumVecRows;
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < kColsumVecRows / 8; ++i) {
+      const long long r = r0 + ty + 8 * i;
+      if (r < rows) {
+        float4 v = ld4<Tin>(dY + r * N + n);
+        if (gate) {
+          const float4 y = ld4<__nv_bfloat16>(Y + r * N + n);
+          v.x = y.x > 0.f ? v.x * scale : 0.f; v.y = y.y > 0.f ? v.y * scale : 0.f;
+          v.z = y.z > 0.f ? v.z * scale : 0.f; v.w = y.w > 0.f ? v.w * scale : 0.f;
+        }
+        st4<__nv_bfloat16>(dZ + r * N + n, v);
+        // sum exactly what the GEMMs will read (the bf16-rounded values)
+        acc[i & 3].x += __bfloat162float(__float2bfloat16_rn(v.x)); acc[i & 3].y += __bfloat162float(__float2bfloat16_rn(v.y));
+        acc[i & 3].z += __bfloat162float(__float2bfloat16_rn(v.z)); acc[i & 3].w += __bfloat162float(__float2bfloat16_rn(v.w));
+      }
+    }
+  }
+  red[ty][tx] = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                            (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float4 t = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { t.x += red[w][tx].x; t.y += red[w][tx].y; t.z += red[w][tx].z; t.w += red[w][tx].w; }
+    *reinterpret_cast<float4*>(part + (long long)blockIdx.y * N + n) = t;
+  }
+}
+// bf16 in / bf16 out variant with 16-byte accesses: a CTA covers [64 rows][256 columns], lane = 8 columns, 8 warps take
+// interleaved rows with all eight 16-byte loads of dY (and of Y) in flight before the first use.
+__global__ void __launch_bounds__(256)
+gate_colsum8_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ Y, __nv_bfloat16* __restrict__ dZ,
+                    float* __restrict__ part, long long rows, int N, float scale, int gate) {
+  pdl_wait();
+  __shared__ float red[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 256 + tx * 8;
+  const long long r0 = (long long)blockIdx.y * 64;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  if (n < N) {
+    uint4 g[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long r = r0 + ty + 8 * i;
+      g[i] = make_uint4(0u, 0u, 0u, 0u); y[i] = g[i];
+      if (r < rows) {
+        g[i] = *reinterpret_cast<const uint4*>(dY + r * N + n);
+        if (gate) y[i] = *reinterpret_cast<const uint4*>(Y + r * N + n);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long r = r0 + ty + 8 * i;
+      if (r < rows) {
+        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g[i]);
+        const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&y[i]);
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 v = __bfloat1622float2(gh[k]);
+          if (gate) {
+            const float2 yv = __bfloat1622float2(yh[k]);
+            v.x = yv.x > 0.f ? v.x * scale : 0.f;
+            v.y = yv.y > 0.f ? v.y * scale : 0.f;
+          }
+          oh[k] = __floats2bfloat162_rn(v.x, v.y);
+          const float2 w = __bfloat1622float2(oh[k]);          // sum exactly what the GEMMs will read
+          acc[2 * k] += w.x; acc[2 * k + 1] += w.y;
+        }
+        *reinterpret_cast<uint4*>(dZ + r * N + n) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[ty][tx * 8 + u] = acc[u];
+  __syncthreads();
+  const int c = threadIdx.x;                       // 256 threads = 256 columns
+  if (blockIdx.x * 256 + c < N) {
+    float t = red[0][c];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][c];
+    part[(long long)blockIdx.y * N + blockIdx.x * 256 + c] = t;
+  }
+}
 // out[n] (+)= sum_c part[c][n]: a CTA owns 32 columns, its 8 warps take interleaved chunks (coalesced 128 B rows of the
 // partial matrix), fixed-order combine through shared memory
 __global__ void __launch_bounds__(256)
@@ -418,6 +519,29 @@ extern "C" int pka_colsum(const void* x, float* out, float* part_ws, int dtype, 
   int rc = check_launch("colsum_part");
   if (rc) return rc;
   launch_k(colsum_finish_kernel, (N + 31) / 32, 256, 0, as_stream(stream), part_ws, out, chunks, N, accumulate);
+  return check_launch("colsum_finish");
+}
+
+extern "C" int pka_gate_colsum(const void* dY, int dy_dtype, const void* Y, void* dZ, float* out, float* part_ws, int64_t rows,
+                               int N, float scale, int gate, void* stream) {
+  PKA_REQUIRE(dY && dZ && out && part_ws && (!gate || Y), PKA_EINVAL, "gate_colsum: null pointer");
+  PKA_REQUIRE(rows > 0 && N > 0 && N % 4 == 0, PKA_EUNSUPPORTED, "gate_colsum: rows=%lld N=%d (need N%%4==0)", (long long)rows, N);
+  PKA_REQUIRE(aligned16(dY) && aligned16(dZ) && aligned16(part_ws) && (!Y || aligned16(Y)), PKA_EALIGN, "gate_colsum: pointers must be 16-byte aligned");
+  int chunks = (int)((rows + kColsumVecRows - 1) / kColsumVecRows);
+  PKA_REQUIRE((rows + 63) / 64 <= 65535, PKA_EUNSUPPORTED, "gate_colsum: too many rows");
+  dim3 grid((N + 127) / 128, chunks);
+  if (dy_dtype == PKA_BF16 && N % 8 == 0) {
+    chunks = (int)((rows + 63) / 64);              // = pka_colsum_chunks(rows): what the workspace is sized for
+    launch_k(gate_colsum8_kernel, dim3((N + 255) / 256, chunks), 256, 0, as_stream(stream), (const __nv_bfloat16*)dY,
+             (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, part_ws, (long long)rows, N, scale, gate);
+  } else if (dy_dtype == PKA_BF16)
+    launch_k(gate_colsum_kernel<__nv_bfloat16>, grid, 256, 0, as_stream(stream), (const __nv_bfloat16*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, part_ws, (long long)rows, N, scale, gate);
+  else if (dy_dtype == PKA_F32)
+    launch_k(gate_colsum_kernel<float>, grid, 256, 0, as_stream(stream), (const float*)dY, (const __nv_bfloat16*)Y, (__nv_bfloat16*)dZ, part_ws, (long long)rows, N, scale, gate);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "gate_colsum: dtype %d", dy_dtype);
+  int rc = check_launch("gate_colsum");
+  if (rc) return rc;
+  launch_k(colsum_finish_kernel, (N + 31) / 32, 256, 0, as_stream(stream), part_ws, out, chunks, N, 0);
   return check_launch("colsum_finish");
 }
 

@@ -737,6 +737,20 @@ def gate_to_bf16(x, Bt, T, N, y=None, scale=1.0):
     return out
 
 
+def gate_colsum(dy, y, scale, bias_like, Bt, T, N):
+    """dz = (y > 0 ? dy*scale : 0) as bf16 [Bt,T,N] (y None: plain bf16 copy) AND the bias gradient sum_rows(dz), one pass."""
+    L.require_cuda(dy, y)
+    dy = dy.contiguous()
+    rows = Bt * T
+    dz = torch.empty(Bt, T, N, device=dy.device, dtype=torch.bfloat16)
+    db = grad_buffer(bias_like)
+    chunks = L.lib().pka_colsum_chunks(C.c_int64(rows))
+    ws = torch.empty(chunks * N, device=dy.device, dtype=torch.float32)
+    L.check(L.lib().pka_gate_colsum(L.ptr(dy), L.dtype_code(dy), L.ptr(y), L.ptr(dz), L.ptr(db), L.ptr(ws), C.c_int64(rows), N,
+                                    C.c_float(scale), int(y is not None), L.stream_ptr()), "gate_colsum")
+    return dz, db
+
+
 def weight_relayout(w2, K, nseg, want_f=True, want_d=True):
     N = w2.shape[0]
     wf = torch.empty(N, nseg * K, device=w2.device, dtype=torch.bfloat16) if want_f else None
@@ -772,24 +786,36 @@ class _LinearTcFn(torch.autograd.Function):
         Bt, T, kin, N, n_ctx, splice, relu, drop, has_bias, wshape = ctx.meta
         dy = dy.contiguous()
         use_drop = drop is not None and drop.on
+        dx = dw = db = None
+        want_db = has_bias and ctx.needs_input_grad[2]
         if relu:
             assert y.dtype == torch.bfloat16
-            dz = gate_to_bf16(dy, Bt, T, N, y=y, scale=(1.0 / (1.0 - drop.p)) if use_drop else 1.0)
+            scale = (1.0 / (1.0 - drop.p)) if use_drop else 1.0
+            if want_db and N % 4 == 0:            # ReLU/dropout gate and bias gradient in one pass over dY
+                dz, db = gate_colsum(dy, y, scale, bias, Bt, T, N)
+                want_db = False
+            else:
+                dz = gate_to_bf16(dy, Bt, T, N, y=y, scale=scale)
         else:
             if use_drop:
                 tmp = torch.empty_like(dy)
                 L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(tmp), L.dtype_code(dy), C.c_int64(dy.numel()),
                                                 _byref_drop(drop), L.stream_ptr()), "dropout_bwd")
                 dy = tmp
-            dz = dy if dy.dtype == torch.bfloat16 else gate_to_bf16(dy, Bt, T, N)
-        dx = dw = db = None
+            if dy.dtype == torch.bfloat16:
+                dz = dy
+            elif want_db and N % 4 == 0:          # fp32 -> bf16 copy and bias gradient in one pass
+                dz, db = gate_colsum(dy, None, 1.0, bias, Bt, T, N)
+                want_db = False
+            else:
+                dz = gate_to_bf16(dy, Bt, T, N)
         if ctx.needs_input_grad[0]:
             dx = gemm_tc_rows(dz, wd, Bt, T, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * N, b_seg_col=N,
                               shift=[-c for c in splice])
         if ctx.needs_input_grad[1]:
             dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
                                accumulate=False).view(wshape)
-        if has_bias and ctx.needs_input_grad[2]:
+        if want_db:
             db = colsum(dz.view(Bt * T, N), out=grad_buffer(bias), accumulate=False)
         return dx, dw, db, None, None, None, None
 

@@ -37,32 +37,48 @@ def _to_device(batch, device, non_blocking=True):
 
 
 class _Prefetcher:
-    """Host->device staging with one batch of look-ahead on a side stream (double buffering): `take()` hands out the
-    staged batch, `release()` + `stage_next()` -- called right after the step's kernels have been launched and before
-    any host sync -- start the H2D copies of the following batch so they overlap the running step (pinned host batches
-    copy asynchronously).  Two sets of device staging buffers are reused while the batch shape stays the same, so the
-    steady state performs no allocation.  The reference copies synchronously inside the step (L/train.py:151-161)."""
+    """Host->device staging a few batches ahead on a side stream: `take()` hands out the oldest staged batch,
+    `release()` + `stage_next()` -- called right after the step's kernels have been launched and before any host sync --
+    start the H2D copies of a later batch so they overlap the running steps (pinned host batches copy asynchronously).
+    `depth + 1` sets of device staging buffers are reused while the batch shape stays the same, so the steady state
+    performs no allocation.  The reference copies synchronously inside the step (L/train.py:151-161)."""
 
     _DTYPES = (torch.float32, torch.uint8, torch.int64, torch.uint8)
 
-    def __init__(self, batch_loader, device):
+    _CACHE = {}    # per device: copy stream, staging buffers, pinned read-back ring -- created once, reused by every epoch
+
+    @classmethod
+    def resources(cls, device, depth):
+        key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), depth)
+        res = cls._CACHE.get(key)
+        if res is None:
+            res = dict(stream=torch.cuda.Stream(device=device), slots=[None] * (depth + 1),
+                       pinned=[torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(depth + 1)])
+            cls._CACHE[key] = res
+        return res
+
+    def __init__(self, batch_loader, device, depth=3):
+        from collections import deque
         self.device = device
-        self.copy_stream = torch.cuda.Stream(device=device)
+        res = self.resources(device, depth)
+        self.copy_stream = res["stream"]
+        self.copy_stream.wait_stream(torch.cuda.current_stream())     # buffers may still be read by the previous epoch
         self.it = iter(batch_loader)
-        self.slots = [None, None]          # device staging buffers
-        self.free_ev = [None, None]        # compute-stream event: the consumer of this slot has finished reading it
+        self.n_slots = depth + 1
+        self.slots = res["slots"]              # device staging buffers
+        self.free_ev = [None] * self.n_slots   # compute-stream event: the consumer of this slot has finished reading it
         self.n = 0
-        self.staged = None
+        self.queue = deque()
         self.cur_slot = None
-        self.stage_next()
+        for _ in range(depth):
+            self.stage_next()
 
     def stage_next(self):
         try:
             batch = next(self.it)
         except StopIteration:
-            self.staged = None
             return
-        slot = self.n % 2
+        slot = self.n % self.n_slots
         self.n += 1
         hosts = []
         for x, dt in zip(batch[1:5], self._DTYPES):
@@ -78,13 +94,12 @@ class _Prefetcher:
                 b.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self.staged = (tuple(bufs), ev, slot)
+        self.queue.append((tuple(bufs), ev, slot))
 
     def take(self):
-        if self.staged is None:
+        if not self.queue:
             return None
-        tensors, ev, slot = self.staged
-        self.staged = None
+        tensors, ev, slot = self.queue.popleft()
         self.cur_slot = slot
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
@@ -125,29 +140,34 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
     totals = torch.zeros(3, device=device, dtype=torch.float64)          # loss, n_correct, n_words
     host_totals = [0.0, 0.0, 0.0]     # sync_every_step: the reference reads loss/accuracy back on every step (L/train.py:203-207)
 
-    feed = _Prefetcher(batch_loader, device)
+    depth = 3                         # steps the host may run ahead of the GPU (absorbs host scheduling hiccups)
+    feed = _Prefetcher(batch_loader, device, depth)
     # sync_every_step: each step's [loss, n_correct, n_words] is copied to pinned host memory right behind the step and
-    # consumed one step later, so the host never drains the GPU queue between steps
-    pinned = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)] if sync_every_step else None
-    pending, n_step = None, 0
+    # consumed a few steps later, so the host never drains the GPU queue between steps
+    pinned = _Prefetcher.resources(device, depth)["pinned"] if sync_every_step else None
+    from collections import deque
+    pending, n_step = deque(), 0
 
     def read_back(vec3):
-        nonlocal pending, n_step
-        buf = pinned[n_step % 2]
+        nonlocal n_step
+        buf = pinned[n_step % (depth + 1)]
         n_step += 1
         buf.copy_(vec3, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        flush()
-        pending = (buf, ev)
+        pending.append((buf, ev))
+        while len(pending) > depth:
+            consume()
+
+    def consume():
+        buf, ev = pending.popleft()
+        ev.synchronize()
+        for k, v in enumerate(buf.tolist()):
+            host_totals[k] += v
 
     def flush():
-        nonlocal pending
-        if pending is not None:
-            pending[1].synchronize()
-            for k, v in enumerate(pending[0].tolist()):
-                host_totals[k] += v
-            pending = None
+        while pending:
+            consume()
 
     while True:
         cur = feed.take()
