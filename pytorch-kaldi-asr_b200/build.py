@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpka_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-              "-DPKA_BUILD"]
+              "-DPKA_BUILD"] + os.environ.get("PKA_NVCC_EXTRA", "").split()
 
 
 def nvcc() -> str:

@@ -301,6 +301,104 @@ attn_bwd_dkv_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ few queries, many keys
+// Beam-search cross-attention (L/decode.py:85-87 re-runs it for every hypothesis; here the beam is the query axis): at
+// most 16 queries per (utterance, head) against all T encoder frames.  The generic kernel above re-stages every K/V tile
+// once per 8 queries; this one makes ONE pass over K and ONE over V per (utterance, head):
+//   phase 1  lane = key: scores of all queries against its key row (Q broadcast from shared memory) -> S[q][j] in smem
+//   phase 2  warp = query: max / sum over the keys, probabilities normalised in place
+//   phase 3  lane = two output columns: out[q][:] += P[q][j] * V[j][:] with coalesced V rows, 8 warps interleave the keys
+// fp32 throughout; rows without an allowed key give 0 / -inf like the generic kernel.
+constexpr int kSqMaxQ = 16;
+template <int D>
+__global__ void __launch_bounds__(256, 2)
+attn_fwd_smallq_kernel(const AttnP p, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                       const uint8_t* __restrict__ kmask, float* __restrict__ out, float* __restrict__ lse, int LkP) {
+  pdl_wait();
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                                  // [16][D]
+  float* S = Qs + kSqMaxQ * D;                     // [16][LkP]
+  float* red = S + kSqMaxQ * LkP;                  // [8][16][D]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint8_t* km = kmask + (long long)b * p.Lk;
+  const float* kb = k + (long long)b * p.Lk * p.ldk + h * D;
+  const float* vb = v + (long long)b * p.Lk * p.ldv + h * D;
+  for (int e = threadIdx.x; e < kSqMaxQ * D; e += 256) {
+    const int qi = e / D, d = e - qi * D;
+    Qs[e] = qi < p.Lq ? q[((long long)b * p.Lq + qi) * p.ldq + h * D + d] : 0.f;
+  }
+  __syncthreads();
+  // ---- phase 1: scores
+  for (int j = threadIdx.x; j < LkP; j += 256) {
+    float s[kSqMaxQ];
+#pragma unroll
+    for (int qi = 0; qi < kSqMaxQ; ++qi) s[qi] = 0.f;
+    const bool ok = j < p.Lk && km[j] != 0;
+    if (ok) {
+      const float4* kr = reinterpret_cast<const float4*>(kb + (long long)j * p.ldk);
+#pragma unroll 4
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kv = kr[d4];
+#pragma unroll
+        for (int qi = 0; qi < kSqMaxQ; ++qi) {
+          const float4 qv = *reinterpret_cast<const float4*>(Qs + qi * D + d4 * 4);
+          s[qi] = fmaf(qv.x, kv.x, s[qi]); s[qi] = fmaf(qv.y, kv.y, s[qi]);
+          s[qi] = fmaf(qv.z, kv.z, s[qi]); s[qi] = fmaf(qv.w, kv.w, s[qi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < kSqMaxQ; ++qi) S[qi * LkP + j] = ok ? s[qi] * p.scale : -CUDART_INF_F;
+  }
+  __syncthreads();
+  // ---- phase 2: softmax over the keys, one warp per query
+  for (int qi = warp; qi < kSqMaxQ; qi += 8) {
+    float* row = S + qi * LkP;
+    float m = -CUDART_INF_F;
+    for (int j = lane; j < LkP; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float l = 0.f;
+    if (m != -CUDART_INF_F)
+      for (int j = lane; j < LkP; j += 32) { const float e = __expf(row[j] - m); row[j] = e; l += e; }
+    l = warp_sum(l);
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    for (int j = lane; j < LkP; j += 32) row[j] = (m != -CUDART_INF_F) ? row[j] * inv : 0.f;
+    if (lane == 0 && qi < p.Lq) lse[((long long)b * p.H + h) * p.Lq + qi] = l > 0.f ? m + __logf(l) : -CUDART_INF_F;
+  }
+  __syncthreads();
+  // ---- phase 3: out = P V
+  constexpr int CPL = D / 32;                      // output columns per lane (D = 64 -> 2)
+  float acc[kSqMaxQ][CPL];
+#pragma unroll
+  for (int qi = 0; qi < kSqMaxQ; ++qi)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[qi][c] = 0.f;
+  for (int j = warp; j < p.Lk; j += 8) {
+    float vv[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) vv[c] = vb[(long long)j * p.ldv + lane * CPL + c];
+#pragma unroll
+    for (int qi = 0; qi < kSqMaxQ; ++qi) {
+      const float pj = S[qi * LkP + j];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[qi][c] = fmaf(pj, vv[c], acc[qi][c]);
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < kSqMaxQ; ++qi)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) red[(warp * kSqMaxQ + qi) * D + lane * CPL + c] = acc[qi][c];
+  __syncthreads();
+  for (int e = threadIdx.x; e < p.Lq * D; e += 256) {
+    const int qi = e / D, d = e - qi * D;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[(w * kSqMaxQ + qi) * D + d];
+    out[((long long)b * p.Lq + qi) * p.ldo + h * D + d] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ optional probs dump
 template <typename T>
 __global__ void attn_probs_kernel(const AttnP p, int D, const T* __restrict__ q, const T* __restrict__ k,
@@ -347,9 +445,30 @@ static int fill(AttnP& p, const pka_attn_desc* d, const char* who) {
     default: { constexpr int DD = 128; CALL; } break;  \
   }
 
+// fp32, <= 16 queries, no band, no dropout, head dim 64, 16-byte aligned rows: the one-pass kernel above
+static bool smallq_ok(const AttnP& p, int D, const void* q, const void* k, const void* v, int* LkP, int* smem) {
+  if (D != 64 || p.Lq > kSqMaxQ || p.use_band || p.drop.p > 0.f) return false;
+  if ((p.ldk & 3) || (p.ldv & 3) || !aligned16(k) || !aligned16(v) || !aligned16(q)) return false;
+  *LkP = (p.Lk + 31) / 32 * 32;
+  *smem = (kSqMaxQ * D + kSqMaxQ * *LkP + 8 * kSqMaxQ * D) * (int)sizeof(float);
+  return *smem <= 200 * 1024 && p.Lk >= 64;
+}
+
 template <typename T>
 static int fwd_t(const AttnP& p, int D, const void* q, const void* k, const void* v, const uint8_t* km, void* out,
                  float* lse, float* probs, cudaStream_t st) {
+  int LkP = 0, smem = 0;
+  if (sizeof(T) == 4 && !probs && smallq_ok(p, D, q, k, v, &LkP, &smem)) {
+    static int smem_set = 0;
+    if (smem > smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_fwd: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+      smem_set = 200 * 1024;
+    }
+    launch_k(attn_fwd_smallq_kernel<64>, dim3(p.H, p.B), 256, (size_t)smem, st, p, (const float*)q, (const float*)k, (const float*)v, km,
+             (float*)out, lse, LkP);
+    return check_launch("attn_fwd(smallq)");
+  }
   dim3 grid((p.Lq + kAttWarps - 1) / kAttWarps, p.H, p.B), block(kAttWarps * 32);
   PKA_ATT_DISPATCH(D, (launch_k(attn_fwd_kernel<T, DD>, grid, block, 0, st, p, (const T*)q, (const T*)k, (const T*)v, km, (T*)out, lse)));
   int rc = check_launch("attn_fwd");

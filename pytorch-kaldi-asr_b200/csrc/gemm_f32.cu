@@ -204,6 +204,72 @@ gemm_f32_kernel(const GemmParams p) {
   }
 }
 
+// Small-M variant for the decoder-step GEMMs (M = live hypotheses, K <= 256): the whole reduction dimension of a
+// [32 rows] x [64 columns] output tile is staged in shared memory with ONE round of 16-byte loads (the generic kernel
+// above pays a global-memory latency per 32-wide K tile, which is all these launches consist of), then each thread owns
+// 4 rows x 2 columns.  Same accumulation order as the generic kernel (one accumulator per output, k ascending).
+constexpr int SM_BM = 32, SM_BN = 64;
+__global__ void __launch_bounds__(256)
+gemm_f32_small_kernel(const GemmParams p) {
+  pdl_wait();
+  extern __shared__ __align__(16) float smf[];
+  const int K = p.K, ldb_s = K + 4;
+  float* As = smf;                                 // [32][K]
+  float* Bs = smf + SM_BM * K;                     // [64][K + 4]
+  const int m_blk = blockIdx.y * SM_BM, n_blk = blockIdx.x * SM_BN;
+  const int k4n = K >> 2;
+  for (int e = threadIdx.x; e < SM_BM * k4n; e += 256) {
+    const int r = e / k4n, c = e - r * k4n, m = m_blk + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < p.M) v = *reinterpret_cast<const float4*>(p.A + (long long)m * p.lda + c * 4);
+    *reinterpret_cast<float4*>(As + r * K + c * 4) = v;
+  }
+  for (int e = threadIdx.x; e < SM_BN * k4n; e += 256) {
+    const int r = e / k4n, c = e - r * k4n, n = n_blk + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < p.N) v = *reinterpret_cast<const float4*>(p.B + (long long)n * p.ldb + c * 4);
+    *reinterpret_cast<float4*>(Bs + r * ldb_s + c * 4) = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+  const float* a0 = As + (ty * 4) * K;
+  const float* b0 = Bs + tx * ldb_s;
+  const float* b1 = Bs + (tx + 32) * ldb_s;
+#pragma unroll 4
+  for (int c = 0; c < k4n; ++c) {
+    const float4 bv0 = *reinterpret_cast<const float4*>(b0 + c * 4);
+    const float4 bv1 = *reinterpret_cast<const float4*>(b1 + c * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 av = *reinterpret_cast<const float4*>(a0 + i * K + c * 4);
+      acc[i][0] = fmaf(av.x, bv0.x, acc[i][0]); acc[i][0] = fmaf(av.y, bv0.y, acc[i][0]);
+      acc[i][0] = fmaf(av.z, bv0.z, acc[i][0]); acc[i][0] = fmaf(av.w, bv0.w, acc[i][0]);
+      acc[i][1] = fmaf(av.x, bv1.x, acc[i][1]); acc[i][1] = fmaf(av.y, bv1.y, acc[i][1]);
+      acc[i][1] = fmaf(av.z, bv1.z, acc[i][1]); acc[i][1] = fmaf(av.w, bv1.w, acc[i][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m_blk + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n_blk + tx + 32 * j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.residual) v += p.residual[(long long)m * p.ldr + n];
+      float* dst = p.C + (long long)m * p.ldc + n;
+      if (p.accumulate) v += *dst;
+      *dst = v;
+    }
+  }
+}
+
 __global__ void splitk_reduce_kernel(const GemmParams p) {
   pdl_wait();
   const long long per = (long long)p.M * p.N, total = per * p.nbatch;
@@ -257,6 +323,20 @@ extern "C" int pka_gemm_f32(const pka_gemm_desc* d, void* stream) {
     PKA_REQUIRE((long long)d->nbatch * p.splitk <= 65535, PKA_EUNSUPPORTED, "gemm_f32: nbatch*splitk too large");
   }
   cudaStream_t st = as_stream(stream);
+  // decoder-step shape: few rows, short reduction, nn.Linear weight layout, no splice / dropout / batching
+  if (!d->transA && d->transB && d->nseg == 1 && d->nbatch == 1 && d->T == 0 && p.splitk == 1 && d->drop.p == 0.f &&
+      d->M <= 4096 && d->K <= 256 && d->K % 4 == 0 && d->lda % 4 == 0 && d->ldb % 4 == 0 && aligned16(d->A) && aligned16(d->B) &&
+      !getenv("PKA_GEMM_NOSMALL")) {
+    const int smem = (SM_BM * d->K + SM_BN * (d->K + 4)) * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_f32_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_f32: cannot opt in to shared memory: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    launch_k(gemm_f32_small_kernel, dim3((d->N + SM_BN - 1) / SM_BN, (d->M + SM_BM - 1) / SM_BM), 256, (size_t)smem, st, p);
+    return check_launch("gemm_f32(small)");
+  }
   // big tiles only when they still give >= ~1 wave of CTAs
   long long big_ctas = (long long)((d->M + 127) / 128) * ((d->N + 127) / 128) * d->nbatch * p.splitk;
   bool big = d->N >= 128 && big_ctas >= kNumSMs;

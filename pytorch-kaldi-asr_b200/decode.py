@@ -76,6 +76,12 @@ class BeamDecoder:
         self.desc.eos, self.desc.force_full_length = constants.EOS, int(force_full_length)
         self.graph = None
         self.steps_run = 0
+        # The weights are frozen while decoding: pack the per-head projection tensors w_p[h, d, j] (T/SubLayers.py:29-31)
+        # once into nn.Linear layout [(p,h,j), d], so q|k|v of a step is ONE GEMM instead of three head-batched ones.
+        # (re-packed into the same buffers on every reset(), so weight updates between batches are picked up and the
+        # captured step graph keeps pointing at valid storage)
+        self.w_qkv = [torch.empty(3 * self.HD, self.D, **f32) for _ in range(self.n_layers)]
+        self.w_q_cross = [torch.empty(self.HD, self.D, **f32) for _ in range(self.n_layers)]
 
     # ------------------------------------------------------------------------------------------------ state
     def reset(self, enc_output: torch.Tensor, src_pad_mask: torch.Tensor):
@@ -97,6 +103,10 @@ class BeamDecoder:
         self.n_not_done.fill_(self.n_utt)
         self.src_mask.copy_(src_pad_mask.to(torch.uint8))
         with torch.no_grad():
+            pack = lambda *ws: torch.cat([w.detach().permute(0, 2, 1).reshape(-1, w.shape[1]) for w in ws])
+            for l, layer in enumerate(self.dec.layer_stack):
+                self.w_qkv[l].copy_(pack(layer.slf_attn.w_qs, layer.slf_attn.w_ks, layer.slf_attn.w_vs))
+                self.w_q_cross[l].copy_(pack(layer.enc_attn.w_qs))
             enc = self.dec.enc_dec_projection(enc_output, out_fp32=True)                      # [n_utt, T, Dd], once (T/Models.py:199)
             for l, layer in enumerate(self.dec.layer_stack):
                 self.enc_kv[l].copy_(ops.head_proj(enc, layer.enc_attn.w_ks, layer.enc_attn.w_vs))
@@ -116,7 +126,7 @@ class BeamDecoder:
         for l, layer in enumerate(dec.layer_stack):
             sa, ca, ff = layer.slf_attn, layer.enc_attn, layer.pos_ffn
             # --- self-attention over the lattice ancestors
-            qkv = ops.head_proj(x, sa.w_qs, sa.w_ks, sa.w_vs)                  # [n, K, 3*HD]
+            qkv = ops.linear(x, self.w_qkv[l])                                 # [n, K, 3*HD]
             ctx = torch.empty(n, K, HD, device=self.dev, dtype=torch.float32)
             qp = qkv.data_ptr()
             L.check(lib.pka_tree_attn(C.c_void_p(qp), C.c_void_p(qp + 4 * HD), C.c_void_p(qp + 8 * HD), 3 * HD,
@@ -129,7 +139,7 @@ class BeamDecoder:
                                           self.E, HD, st()), "kv_append")
             x = self._post(sa.proj, ctx, x, sa.layer_norm, skip_ln)
             # --- cross-attention: the beam is the query axis, K/V shared per utterance
-            q = ops.head_proj(x, ca.w_qs)
+            q = ops.linear(x, self.w_q_cross[l])
             ctx, _ = ops.attention(q, self.enc_kv[l], self.src_mask, self.H, self.dk, None, scale, None)
             x = self._post(ca.proj, ctx, x, ca.layer_norm, skip_ln)
             # --- position-wise FFN
