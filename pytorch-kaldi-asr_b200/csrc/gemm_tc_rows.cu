@@ -420,18 +420,28 @@ static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
   const int tiles_m = d->Bt * ((d->T + R2_BM - 1) / R2_BM);
   // CTA-pair mode (cta_group::2, M = 256): each CTA stages only HALF of every weight tile, which halves the dominant
   // shared-memory ingress.  Needs equal column chunks of <= 256 that are multiples of 64, all in one CTA's 512 TMEM columns.
-  int pair = 0, nt = 0, chunk = R2_BN;
+  int pair = 0, nt = 0, chunk = R2_BN, pair_gy = 1;
+  const int budget0 = 225 * 1024 - a_bytes - 2 * R2_C_BYTES - 256 - 2048 - 64;
   if (tiles_m >= 2) {
-    // 128-column chunks when possible: the epilogue of chunk n overlaps the MMAs of chunk n+1
-    if (d->N % 256 == 0 && d->N <= 512) { pair = 1; nt = d->N / 256; chunk = 256; }        // largest TMA boxes (16 KB)
-    else if (d->N % 128 == 0 && d->N <= 512) { pair = 1; nt = d->N / 128; chunk = 128; }
-    else if (d->N <= 256 && d->N % 64 == 0) { pair = 1; nt = 1; chunk = d->N; }
-    if (const char* e = getenv("PKA_TC_CHUNK")) { const int c = atoi(e); if (pair && c >= 64 && c <= 256 && c % 64 == 0 && d->N % c == 0 && d->N <= 512) { chunk = c; nt = d->N / c; } }
+    // Column chunk candidates, widest first (16 KB TMA boxes); a CTA covers up to 512 columns (its TMEM), wider outputs
+    // go over grid.y.  The weight ring must hold >= 3 stages next to the resident activations (>= 2 as a last resort):
+    // with d_model = 512 activations (128 KB) only the 128-column chunks (16 KB stages) fit.
+    int cand[3] = {256, 128, (d->N <= 256 && d->N % 64 == 0) ? d->N : 0};
+    if (const char* e = getenv("PKA_TC_CHUNK")) { const int c = atoi(e); if (c >= 64 && c <= 256 && c % 64 == 0) { cand[0] = c; cand[1] = 0; cand[2] = 0; } }
+    for (int need = 3; need >= 2 && !pair; --need)
+      for (int ci = 0; ci < 3 && !pair; ++ci) {
+        const int c = cand[ci];
+        if (c <= 0 || d->N % c != 0) continue;
+        const int per_cta = d->N < 512 ? d->N : 512;
+        if (per_cta % c != 0 || d->N % per_cta != 0) continue;
+        if (budget0 / (c * 128) < need) continue;
+        pair = 1; chunk = c; nt = per_cta / c; pair_gy = d->N / per_cta;
+      }
   }
   if (const char* e = getenv("PKA_TC_PAIR")) pair = pair && atoi(e) != 0;
   pl->pair = pair;
   if (pair) {
-    pl->nt = nt; pl->chunk = chunk; pl->grid_y = 1;
+    pl->nt = nt; pl->chunk = chunk; pl->grid_y = pair_gy;
     pl->stage_bytes = chunk * 128;                                       // two boxes of [chunk/2 rows][64]
   } else {
     const int n_tiles_n = (d->N + R2_BN - 1) / R2_BN;
@@ -441,8 +451,7 @@ static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
     if (pl->grid_y > 1 && n_tiles_n % R2_MAX_NT != 0) return false;    // keep every grid row on the same tile count
     pl->stage_bytes = R2_STAGE_BYTES;
   }
-  const int budget = 225 * 1024 - a_bytes - 2 * R2_C_BYTES - 256 - 2048 - 64;
-  int stages = budget / pl->stage_bytes;
+  int stages = budget0 / pl->stage_bytes;
   if (stages > R2_MAX_STAGES) stages = R2_MAX_STAGES;
   if (stages < 2) return false;
   const int total = pl->nt * d->nseg * ((kb + 1) / 2);

@@ -37,6 +37,8 @@ def rnd(*shape, seed=0, scale=1.0):
     (4, 499, 256, 256, [-3, 0, 3], True, True),  # TDNN layer at TIMIT size, splice by shifted TMA boxes
     (5, 130, 256, 256, [-1, 0, 1], True, True),
     (2, 300, 256, 128, None, False, False),      # enc_dec_projection
+    (3, 333, 512, 512, None, True, True),        # config-5 FFN: 128 KB of resident activations, 128-column chunks
+    (2, 200, 512, 1536, None, False, False),     # config-5 packed q|k|v projection: output columns over grid.y
 ])
 def test_linear_tc_fwd_bwd(Bt, T, kin, N, ctx, relu, bias):
     from pytorch_kaldi_asr_b200 import ops
