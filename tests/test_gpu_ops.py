@@ -357,3 +357,15 @@ def test_fused_adam_matches_oracle_adam_and_schedule():
     assert opt.n_current_steps == 5
     assert int(opt.optimizer.dev_state[0]) == 5 and int(opt.optimizer.dev_state[1]) == 5
     assert abs(float(opt.optimizer.dev_lr[0]) - osch.lr) < 1e-9
+
+
+@pytest.mark.parametrize("p,site,seed,step,n", [(0.35, 3, 1234, 7, 100003), (0.1, 24, (0xdeadbeef << 32) | 17, (5 << 32) | 9, 4099),
+                                                (0.999, 1, 1, 1, 257), (0.5, 0, 0, 0, 64)])
+def test_dropout_bits_equal_the_numpy_philox_restatement(p, site, seed, step, n):
+    """The keep bits every kernel derives (pka_dropout_mask materialises them) are bit-identical to oracle/philox.py,
+    which reproduces the published Philox4x32-10 known-answer vectors (CPU test)."""
+    from oracle import philox
+    o = ops()
+    st = torch.tensor([step], dtype=torch.int64, device=DEV)
+    got = o.dropout_keep_mask(n, o.Drop(p, site, seed, st), DEV).cpu().numpy()
+    assert np.array_equal(got, philox.keep_mask(n, p, site, seed, step))

@@ -184,3 +184,21 @@ def test_beam_decode_tokens_and_scores(beam, nbest, max_len):
         for j, seq in enumerate(hyps[u]):
             assert seq == g[tag + "hyp.%d.%d" % (u, j)].tolist()
         close(np.asarray(weights[u]), g[tag + "weights.%d" % u], rtol=1e-5, atol=2e-5)
+
+
+def test_philox_restatement_matches_the_published_known_answer_vectors():
+    """oracle/philox.py (the keep-bit definition the kernels are checked against) reproduces the Random123
+    Philox4x32-10 known-answer vectors."""
+    from oracle import philox
+    kat = [
+        (0, 0, 0, 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        (0xffffffffffffffff, 0xffffffff, 0xffffffff, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x299f31d0 << 32) | 0xa4093822, 0x13198a2e, 0x03707344, (0x85a308d3 << 32) | 0x243f6a88,
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for seed, site, step, idx, want in kat:
+        got = philox.philox4x32_10(seed, site, step, np.array([idx], dtype=np.uint64))[0]
+        assert tuple(int(x) for x in got) == want
+    m = philox.keep_mask(200000, 0.35, 3, 1234, 7)
+    assert abs(m.mean() - 0.65) < 5e-3
+    assert philox.keep_mask(10, 0.0, 1, 2, 3).all()
