@@ -37,6 +37,12 @@ struct AttnTcP {
   pka_dropout drop;
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {       // MUFU.EX2 (2 ulp); exp2f() adds range fix-ups around it
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr uint32_t kIdescS = make_idesc(AT_BM, AT_BN);                  // S = Q K^T
 constexpr uint32_t kIdescO = make_idesc(AT_BM, AT_D, false, true);      // O = P V  (V is MN-major)
 
@@ -136,21 +142,34 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
     uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
 
-    for (int j = 0; j < n_tiles; ++j) {
-      const int j0 = (tile_lo + j) * AT_BN;
-      // allowed-key bit masks of this row for the 4 chunks of 32 keys
-      uint32_t allow[4];
+    // allowed-key bit masks (key padding by warp ballot, band as a per-row bit range) and dropout keep bits of this
+    // row for the 4 chunks of 32 keys of a tile.  Both depend on indices only, so the masks of tile j+1 are built while
+    // the tensor core runs P_j V_j (the thread would otherwise just wait for that product).
+    uint32_t allow[4], keep[4];
+    auto tile_masks = [&](int jt, uint32_t (&al)[4], uint32_t (&kp)[4]) {
+      const int jb = (tile_lo + jt) * AT_BN;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int jj = j0 + c * 32 + lane;
+        const int jj = jb + c * 32 + lane;
         const uint32_t kbits = __ballot_sync(0xffffffffu, jj < p.Lk && km[jj] != 0);
         uint32_t bm = 0xffffffffu;
         if (p.use_band) {
-          const int lo = max(0, i + p.start - (j0 + c * 32)), hi = min(31, i + p.end - (j0 + c * 32));
+          const int lo = max(0, i + p.start - (jb + c * 32)), hi = min(31, i + p.end - (jb + c * 32));
           bm = (hi >= lo) ? ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
         }
-        allow[c] = row_ok ? (kbits & bm) : 0u;
+        al[c] = row_ok ? (kbits & bm) : 0u;
+        kp[c] = 0xffffffffu;
+        if (dc.p > 0.f && al[c] != 0u) {           // one Philox call per 8 consecutive keys (row pitch Lk8 % 8 == 0)
+          uint32_t kb = 0u;
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) kb |= dropout_bits8(dc, (drop_row + (unsigned long long)(jb + c * 32 + e)) >> 3) << e;
+          kp[c] = kb;
+        }
       }
+    };
+    if (n_tiles > 0) tile_masks(0, allow, keep);
+
+    for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(smem_u32(&bars[5]), j & 1);
       tc_fence_after();
       // pass 1: tile maximum of the scaled scores (exp2 domain)
@@ -165,7 +184,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       const float m_new = fmaxf(m_run, t_max);
       const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = (m_run == -CUDART_INF_F) ? 0.f : exp2f(m_run - m_new);
+      const float alpha = (m_run == -CUDART_INF_F) ? 0.f : fast_exp2(m_run - m_new);
       // pass 2: probabilities -> bf16 P tile in shared memory (UMMA K-major, 128B swizzle)
       float l_tile = 0.f;
 #pragma unroll
@@ -175,17 +194,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         float pv[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const float pe = ((allow[c] >> e) & 1u) ? exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use)) : 0.f;
+          const float pe = ((allow[c] >> e) & 1u) ? fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use)) : 0.f;
           l_tile += pe;
           pv[e] = pe;
         }
-        if (dc.p > 0.f && allow[c] != 0u) {        // one Philox call per 8 consecutive keys (row pitch Lk8 % 8 == 0)
+        if (dc.p > 0.f) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            const uint32_t kb = dropout_bits8(dc, (drop_row + (unsigned long long)(j0 + c * 32 + e)) >> 3);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pv[e + u] = ((kb >> u) & 1u) ? pv[e + u] * dc.scale : 0.f;
-          }
+          for (int e = 0; e < 32; ++e) pv[e] = ((keep[c] >> e) & 1u) ? pv[e] * dc.scale : 0.f;
         }
         uint8_t* pblk = prow + (c >> 1) * (AT_BM * 128);
 #pragma unroll
@@ -203,6 +218,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       mbar_arrive(smem_u32(&bars[6]));
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
+      if (j + 1 < n_tiles) tile_masks(j + 1, allow, keep);       // overlaps the P_j V_j MMAs
       // O = alpha * O + P_j V_j
       mbar_wait(smem_u32(&bars[7]), j & 1);
       tc_fence_after();
