@@ -388,7 +388,7 @@ def run_b200(args):
                                 for x, dt in zip(b[1:], (torch.float32, torch.uint8, torch.int64, torch.uint8)))
                 for b in pool]
     n_buckets = int(os.environ.get("PKA_BUCKETS", "3"))
-    sync = parallel.GradAllReduce(opt.optimizer, n_buckets=n_buckets) if world > 1 else None
+    sync = parallel.GradAllReduce(opt.optimizer, n_buckets=n_buckets, backend=os.environ.get("PKA_ALLREDUCE", "nccl")) if world > 1 else None
     launches0 = _lib.launch_count()
     graphed, graph_note = None, "eager"
     if not args.no_graph:
