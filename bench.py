@@ -219,8 +219,15 @@ def roofline_probe(model, B, T, pk, mode):
         sec = time_kernel(fwd)
         out["kernel"] = "gemm_f32_kernel<128,128,32,8,8> (TDNN splice+Linear+bias+ReLU, fp32 SIMT exact path)"
     achieved = flops / sec / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")      # DRAM bytes per launch from the committed ncu capture
+    if mode == "bf16" and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     out.update({"bound": "tensor", "achieved": achieved, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk_["bf16_tflops"], "traffic": None, "peak_source": pk_["source"] + " bf16 burst",
+                "frac": achieved / pk_["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk_["source"] + " bf16 burst",
                 "us_per_launch": sec * 1e6, "flops_per_launch": flops})
     return out
 

@@ -143,3 +143,58 @@ def test_attention_encoder_model_bf16_vs_oracle():
     cos = {k: cosine(p.grad, grads_ref[k]) for k, p in model.named_parameters() if k in grads_ref}
     bad = {k: round(v, 5) for k, v in cos.items() if v < 0.99}
     assert not bad, "gradient cosines below the stated bound: %r" % bad
+
+
+@pytest.mark.parametrize("dy_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("gate", [True, False])
+def test_gate_colsum_one_pass_matches_separate_ops(dy_dtype, gate):
+    """Fused ReLU/dropout gate + bias gradient: dZ identical to the stand-alone gate kernel, bias gradient = column sums of
+    the bf16-rounded dZ (1e-5 of its scale: only the summation order differs)."""
+    from pytorch_kaldi_asr_b200 import ops
+    Bt, T, N = 3, 211, 256
+    dy = rnd(Bt, T, N, seed=11).to(dy_dtype).to(DEV)
+    y = (rnd(Bt, T, N, seed=12).clamp(min=0)).bfloat16().to(DEV) if gate else None
+    bias = torch.zeros(N, device=DEV)
+    dz, db = ops.gate_colsum(dy, y, 1.0 / 0.65 if gate else 1.0, bias, Bt, T, N)
+    want = dy.float()
+    if gate:
+        want = torch.where(y.float() > 0, want * (1.0 / 0.65), torch.zeros_like(want))
+    want = want.bfloat16()
+    assert torch.equal(dz, want)
+    ref = want.float().sum(dim=(0, 1))
+    assert rel_err(db, ref) <= 1e-5
+
+
+def test_backward_writes_gradients_straight_into_the_adam_arena():
+    """With a FusedAdam and zero_grad() (set_to_none) every parameter gradient produced by the backward kernels IS its
+    slot of the flat gradient arena (no accumulate kernels, no copies), and equals the gradient of the plain path."""
+    import pytorch_kaldi_asr_b200 as pk
+    from pytorch_kaldi_asr_b200.utils import synthetic
+    cfg = am.example_config(en_dropout=0.0, de_dropout=0.0)
+    lda = synthetic.lda_matrix()
+    sd = am.init_state_dict(cfg, lda, seed=0)
+    batch = synthetic.batches(1, 3, seed=5)[0]
+    grads = {}
+    for with_opt in (False, True):
+        model = pk.Transformer(lda_mat=lda, **{k: v for k, v in cfg.items() if k != "encoder_type"})
+        model.load_state_dict(sd)
+        model = model.to(DEV).eval()
+        opt = pk.FusedAdam(model.parameters()) if with_opt else None
+        if opt is not None:
+            opt.zero_grad()
+            assert all(p.grad is None for p in opt._train)
+        pk.set_compute_mode("bf16")
+        try:
+            src, smask, tgt, tmask = pk.train._to_device(batch, DEV)
+            pred = model(src, smask, tgt[:, :-1], tmask[:, :-1])
+            loss, _ = pk.get_performance(None, pred, tgt[:, 1:], smoothing=False)
+            loss.backward()
+        finally:
+            pk.set_compute_mode("fp32")
+        if opt is not None:
+            for p, off in zip(opt._train, opt._offsets):
+                assert p.grad is not None and p.grad.data_ptr() == opt.flat_grad[off:off + 1].data_ptr()
+        grads[with_opt] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    assert grads[False].keys() == grads[True].keys()
+    for k in grads[False]:
+        assert torch.equal(grads[False][k], grads[True][k]), k
