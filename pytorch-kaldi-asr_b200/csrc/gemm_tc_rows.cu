@@ -271,7 +271,11 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const long long m = (long long)b0 * p.T + t;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint8_t* sCg = sC + grp * R2_C_BYTES;
-    uint8_t* crow = sCg + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    // Once the LAST accumulator is complete every MMA has read the weight ring and nothing writes it any more, so the
+    // ring itself serves as staging: each 64-column slice of the last chunk gets its own 16 KB tile and its bulk store
+    // never has to wait for an earlier one (the two per-group tiles of sC serve the chunks that overlap the MMAs).
+    const bool ring_ok = p.stages * p.stage_bytes >= (p.chunk >> 6) * R2_C_BYTES;
     bool store_pending = false;
     // Dropout keep bits depend only on (row, column), not on the accumulators: generate them NOW, while the MMAs run,
     // so that the Philox rounds are off the exposed epilogue (1 bit per element, <= 256 columns per thread).
@@ -313,7 +317,10 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       for (int hf = grp; hf < (p.chunk >> 6); hf += 2) { // 64 output columns at a time
         const int nb0 = nbase + nt * p.chunk + hf * 64;
         if (nb0 >= p.N) break;
-        if (p.tma_store) {
+        const bool in_ring = ring_ok && nt == p.nt - 1;
+        uint8_t* tile = in_ring ? sB + hf * R2_C_BYTES : sCg;
+        uint8_t* crow = tile + row_off;
+        if (p.tma_store && !in_ring) {
           if (store_pending) {                     // the previous bulk store must have read the staging tile
             if (gtid == 0) tma_store_wait_read();
             if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -382,8 +389,8 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (p.tma_store) {
           fence_async_smem();
           if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (gtid == 0 && tile_ok && !(p.dbg & 4)) tma_store_3d(&mapC, smem_u32(sCg), nb0, t0, b0);   // rows >= T are clipped
-          store_pending = true;
+          if (gtid == 0 && tile_ok && !(p.dbg & 4)) tma_store_3d(&mapC, smem_u32(tile), nb0, t0, b0);   // rows >= T are clipped
+          if (!in_ring) store_pending = true;
         }
       }
     }
@@ -456,6 +463,8 @@ static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
   if (stages < 2) return false;
   const int total = pl->nt * d->nseg * ((kb + 1) / 2);
   if (stages > total) stages = total;
+  const int ring_min = ((pl->chunk >> 6) * R2_C_BYTES + pl->stage_bytes - 1) / pl->stage_bytes;   // epilogue staging of the last chunk
+  if (stages < ring_min && ring_min * pl->stage_bytes <= budget0) stages = ring_min;
   pl->stages = stages;
   pl->smem = a_bytes + stages * pl->stage_bytes + 2 * R2_C_BYTES + 256 + 2048;
   if (pl->smem < 116 * 1024) pl->smem = 116 * 1024;                      // one CTA per SM: it owns all 512 TMEM columns
