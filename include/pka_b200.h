@@ -126,6 +126,9 @@ int pka_head_weight_relayout(const float* w0, const float* w1, const float* w2, 
                              void* Wd, void* stream);
 int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, float* g2, int P, int H, int D, int dk,
                            void* stream);
+/* pka_tc_reduce + pka_head_grad_relayout in one launch: g_p[h,d,j] = sum_{s<splits} ws[s][(p*H+h)*dk+j][d] (fixed order) */
+int pka_tc_reduce_heads(const float* ws, float* g0, float* g1, float* g2, int splits, int P, int H, int D, int dk,
+                        void* stream);
 /* dZ = gate ? ((Y > 0) ? dY*scale : 0) : dY, bf16, written row-major [Bt*T, N] (dZ) and transposed [N, Bt, Tp] (dZt) */
 int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, void* dZ, void* dZt, int Bt, int T, int Tp, int N,
                       float scale, int gate, void* stream);

@@ -58,5 +58,9 @@ class LDALayer(nn.Module):
 
     def forward(self, x):
         if x.dtype == torch.bfloat16:
-            return ops.affine_tc(x, self.weight, self.bias)
+            # frozen matrix: its bf16 [out, in] operand copy is made once and lives with the module
+            key = (self.weight._version, self.weight.data_ptr())
+            if getattr(self, "_wt_key", None) != key:
+                self._wt, self._wt_key = ops.transpose_to_bf16(self.weight), key
+            return ops.affine_tc(x, self.weight, self.bias, wt=self._wt)
         return ops.affine_kn(x, self.weight, self.bias)

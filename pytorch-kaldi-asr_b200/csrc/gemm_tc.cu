@@ -498,6 +498,32 @@ extern "C" int pka_head_weight_relayout(const float* w0, const float* w1, const 
   return check_launch("head_weight_relayout");
 }
 
+// fixed-order sum of the split partials of a packed head-projection weight gradient, written straight in the
+// reference's per-head layout: g_p[h, d, j] = sum_s ws[s][(p*H + h)*dk + j][d]   (tc_reduce + head_grad_relayout in one)
+__global__ void tc_reduce_heads_kernel(HeadPtrs hp, const float* __restrict__ ws, int splits, int P, int H, int D, int dk) {
+  pdl_wait();
+  const long long per = (long long)P * H * dk * D;            // elements of one partial [(p,h,j), d]
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < per; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const int n = (int)(e / D);
+    const int j = n % dk, h = (n / dk) % H, pidx = n / (dk * H);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += ws[(long long)sp * per + e];
+    if (hp.g[pidx]) hp.g[pidx][((long long)h * D + d) * dk + j] = s;
+  }
+}
+
+extern "C" int pka_tc_reduce_heads(const float* ws, float* g0, float* g1, float* g2, int splits, int P, int H, int D, int dk,
+                                   void* stream) {
+  PKA_REQUIRE(ws && splits >= 1 && P >= 1 && P <= 3 && H > 0 && D > 0 && dk > 0, PKA_EINVAL, "tc_reduce_heads: bad arguments");
+  HeadPtrs hp; hp.w[0] = hp.w[1] = hp.w[2] = nullptr; hp.g[0] = g0; hp.g[1] = g1; hp.g[2] = g2;
+  const long long total = (long long)P * H * D * dk;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  launch_k(tc_reduce_heads_kernel, (int)blocks, 256, 0, as_stream(stream), hp, ws, splits, P, H, D, dk);
+  return check_launch("tc_reduce_heads");
+}
+
 extern "C" int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, float* g2, int P, int H, int D, int dk,
                                       void* stream) {
   PKA_REQUIRE(dWcat && P >= 1 && P <= 3, PKA_EINVAL, "head_grad_relayout: bad arguments");

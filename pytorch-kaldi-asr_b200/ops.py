@@ -302,11 +302,11 @@ class _HeadProjFn(torch.autograd.Function):
             dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot)
         dws = [None] * P
         if any(ctx.needs_input_grad[1:1 + P]):
-            dwcat = gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,))
+            part, splits = gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,), reduce=False)
             dws = [grad_buffer(ws[p]) if ctx.needs_input_grad[1 + p] else None for p in range(P)]
             gp = [L.ptr(g) for g in dws] + [C.c_void_p(0)] * (3 - P)
-            L.check(L.lib().pka_head_grad_relayout(L.ptr(dwcat), gp[0], gp[1], gp[2], P, H, D, dk, L.stream_ptr()),
-                    "head_grad_relayout")
+            L.check(L.lib().pka_tc_reduce_heads(L.ptr(part), gp[0], gp[1], gp[2], splits, P, H, D, dk, L.stream_ptr()),
+                    "tc_reduce_heads")
         return (dx, *dws)
 
     @staticmethod
@@ -697,7 +697,7 @@ def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col
     return Cout
 
 
-def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None):
+def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, reduce=True):
     """mode 2: dW[o, seg*N+i] = sum_{b,t} dZ[b,t,o] * X[b,t+shift[seg],i] -> fp32 [M, nseg*N], straight from the row-major
     activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
     split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic)."""
@@ -720,6 +720,8 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None):
     d.relu, d.c_dtype, d.splits = 0, L.PKA_F32, splits
     d.drop = L.NO_DROPOUT
     L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
+    if not reduce:
+        return ws, splits                         # the caller sums the split partials itself (fused with its relayout)
     acc = (out is not None) if accumulate is None else bool(accumulate)
     if out is None:
         out = torch.empty(M, nseg * N, device=dZ.device, dtype=torch.float32)
@@ -824,11 +826,20 @@ def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32
     return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32)
 
 
-def affine_tc(x, weight_kn, bias=None):
-    """Frozen LDA affine on the tensor cores: x bf16 [Bt,T,K] @ W[K,N] + b -> bf16.  No autograd."""
-    Bt, T, K = x.shape
-    N = weight_kn.shape[1]
-    wt = torch.empty(N, K, device=x.device, dtype=torch.bfloat16)
+def transpose_to_bf16(weight_kn):
+    """[K, N] fp32 -> [N, K] bf16 (nn.Linear layout of a matrix stored input-major, e.g. the LDA transform)."""
+    K, N = weight_kn.shape
+    wt = torch.empty(N, K, device=weight_kn.device, dtype=torch.bfloat16)
     L.check(L.lib().pka_transpose(L.ptr(weight_kn.detach().contiguous()), L.PKA_F32, L.ptr(wt), L.PKA_BF16, K, N, L.stream_ptr()),
             "transpose")
+    return wt
+
+
+def affine_tc(x, weight_kn, bias=None, wt=None):
+    """Frozen LDA affine on the tensor cores: x bf16 [Bt,T,K] @ W[K,N] + b -> bf16.  No autograd.  `wt` = cached
+    transpose_to_bf16(weight_kn) (the matrix is frozen, so callers keep it across steps)."""
+    Bt, T, K = x.shape
+    N = weight_kn.shape[1]
+    if wt is None:
+        wt = transpose_to_bf16(weight_kn)
     return gemm_tc_rows(x.detach(), wt, Bt, T, N, K, lda=K, ldb=K, bias=bias.detach() if bias is not None else None)
