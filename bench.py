@@ -366,13 +366,23 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"                     # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
+        # communicator creation prints an "NCCL version" banner on stdout: route fd 1 to stderr until the first
+        # collective is through, so that stdout carries exactly ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if rank == 0:
+                ensure_library()
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    elif rank == 0:
         ensure_library()
-    if world > 1:
-        dist.barrier()
     import pytorch_kaldi_asr_b200 as pk
     from pytorch_kaldi_asr_b200 import _lib, parallel
     from pytorch_kaldi_asr_b200.utils import synthetic
