@@ -8,8 +8,9 @@ The reference scripts (L/train.py, L/decode.py, L/initialize_model.py) import th
     from utils import constants, instances_handler
 
 `import pytorch_kaldi_asr_b200.dropin` (before those lines) registers the B200 implementations under exactly these
-names, so the scripts run unchanged apart from that one import.  `utils.BatchLoader` / `kaldi_io` (Kaldi file I/O) are
-NOT provided -- they are outside the hot path and keep coming from the reference tree.
+names, so the scripts run unchanged apart from that one import.  `utils.BatchLoader` (U/BatchLoader.py) resolves to
+the loader of this package, and -- only when the external `kaldi_io` package the reference depends on is not
+installed -- `kaldi_io` resolves to `utils/kaldi_ark.py` (`read_mat`, `read_mat_scp`, `read_mat_ark`).
 """
 import sys
 
@@ -18,7 +19,7 @@ from . import transformer as _transformer
 from . import utils as _utils
 from .transformer import Lattice as _lattice, Layers as _layers, Models as _models, Modules as _modules
 from .transformer import Optim as _optim, SubLayers as _sublayers
-from .utils import constants as _constants, instances_handler as _ih
+from .utils import BatchLoader as _batch_loader, constants as _constants, instances_handler as _ih, kaldi_ark as _ark
 
 
 def install(override_utils: bool = False):
@@ -31,6 +32,11 @@ def install(override_utils: bool = False):
         sys.modules.setdefault("utils", _utils)
         sys.modules.setdefault("utils.constants", _constants)
         sys.modules.setdefault("utils.instances_handler", _ih)
+        sys.modules.setdefault("utils.BatchLoader", _batch_loader)
+    if "kaldi_io" not in sys.modules:
+        import importlib.util
+        if importlib.util.find_spec("kaldi_io") is None:
+            sys.modules["kaldi_io"] = _ark
 
 
 install()

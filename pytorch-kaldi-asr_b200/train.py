@@ -28,6 +28,30 @@ def get_performance(crit, pred, goal, smoothing=True, num_class=None):
     return loss, stats[0]
 
 
+def initialize_batch_loader(read_feats_scp_file, read_text_file, read_vocab_file, batch_size, mode='drop', **loader_kw):
+    """feats.scp + text + vocab -> BatchLoader over the utterances that have both features and a transcript
+    (L/train.py:20-55): labels become [BOS] + vocabulary indices (UNK for unknown words) + [EOS].  `loader_kw` goes to
+    `utils.BatchLoader.BatchLoader` (pad_to, bucket, seed, shard, ...); the defaults are the reference's: pre-loaded,
+    silent, whole-set padding."""
+    from .utils import instances_handler, kaldi_ark
+    from .utils.BatchLoader import BatchLoader
+    utterances = kaldi_ark.read_scp(read_feats_scp_file)
+    print('[INFO] get {} utterances from {}.'.format(len(utterances), read_feats_scp_file))
+    label_text = {}
+    with open(read_text_file, encoding='utf-8') as f:
+        for line in f:
+            fields = line.split()
+            if fields:
+                label_text[fields[0]] = fields[1:]
+    print('[INFO] get {} labels from {}.'.format(len(label_text), read_text_file))
+    label = instances_handler.apply_vocab(instances_handler.add_control_words(label_text), read_vocab_file, 'word2idx')
+    trainning_triples = [(key, rx, label[key]) for key, rx in utterances.items() if key in label]
+    print('[INFO] match {} utterance-label pairs.'.format(len(trainning_triples)))
+    loader_kw.setdefault('pre_load', True)
+    loader_kw.setdefault('print_info', False)
+    return BatchLoader(trainning_triples, batch_size, mode=mode, **loader_kw)
+
+
 def _to_device(batch, device, non_blocking=True):
     """numpy batch tuple -> device tensors (the reference's FloatTensor/ByteTensor/LongTensor + .cuda(), L/train.py:151-161)."""
     def put(x, dtype):
@@ -44,6 +68,7 @@ class _Prefetcher:
     performs no allocation.  The reference copies synchronously inside the step (L/train.py:151-161)."""
 
     _DTYPES = (torch.float32, torch.uint8, torch.int64, torch.uint8)
+    _NP_DTYPES = (np.float32, np.uint8, np.int64, np.uint8)
 
     _CACHE = {}    # per device: copy stream, staging buffers, pinned read-back ring -- created once, reused by every epoch
 
@@ -53,6 +78,7 @@ class _Prefetcher:
         res = cls._CACHE.get(key)
         if res is None:
             res = dict(stream=torch.cuda.Stream(device=device), slots=[None] * (depth + 1),
+                       host=[[None] * 4 for _ in range(depth + 1)], copied_ev=[None] * (depth + 1),
                        pinned=[torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(depth + 1)])
             cls._CACHE[key] = res
         return res
@@ -66,6 +92,9 @@ class _Prefetcher:
         self.it = iter(batch_loader)
         self.n_slots = depth + 1
         self.slots = res["slots"]              # device staging buffers
+        self.host = res["host"]                # pinned host staging (flat, grow-only), used with loader.next_into
+        self.copied_ev = res["copied_ev"]      # copy-stream event: this slot's H2D copy has left the host buffers
+        self.next_into = getattr(self.it, "next_into", None)
         self.free_ev = [None] * self.n_slots   # compute-stream event: the consumer of this slot has finished reading it
         self.n = 0
         self.queue = deque()
@@ -73,16 +102,39 @@ class _Prefetcher:
         for _ in range(depth):
             self.stage_next()
 
+    def _pinned_alloc(self, slot):
+        """Destination buffers for `loader.next_into`: views of this slot's grow-only pinned host memory, handed out once
+        the slot's previous H2D copy has completed, so the loader writes each batch exactly once on the host."""
+        def alloc(specs):
+            if self.copied_ev[slot] is not None:
+                self.copied_ev[slot].synchronize()
+            flats = self.host[slot]
+            views = []
+            for k, (shape, dt) in enumerate(specs):
+                tdt = self._DTYPES[k]
+                if np.dtype(dt) != np.dtype(self._NP_DTYPES[k]):
+                    raise TypeError("next_into: buffer %d must be %s" % (k, np.dtype(self._NP_DTYPES[k])))
+                numel = int(np.prod(shape))
+                if flats[k] is None or flats[k].numel() < numel:
+                    flats[k] = torch.empty(max(numel, 1), dtype=tdt, pin_memory=True)
+                views.append(flats[k][:numel].view(tuple(shape)))
+            self._views = views
+            return [v.numpy() for v in views]
+        return alloc
+
     def stage_next(self):
+        slot = self.n % self.n_slots
         try:
-            batch = next(self.it)
+            if self.next_into is not None:
+                self.next_into(self._pinned_alloc(slot))
+                hosts = self._views
+            else:
+                batch = next(self.it)
+                hosts = [x.to(dt) if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x), dtype=dt)
+                         for x, dt in zip(batch[1:5], self._DTYPES)]
         except StopIteration:
             return
-        slot = self.n % self.n_slots
         self.n += 1
-        hosts = []
-        for x, dt in zip(batch[1:5], self._DTYPES):
-            hosts.append(x.to(dt) if torch.is_tensor(x) else torch.as_tensor(np.ascontiguousarray(x), dtype=dt))
         with torch.cuda.stream(self.copy_stream):
             if self.free_ev[slot] is not None:
                 self.copy_stream.wait_event(self.free_ev[slot])
@@ -94,6 +146,7 @@ class _Prefetcher:
                 b.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
+        self.copied_ev[slot] = ev
         self.queue.append((tuple(bufs), ev, slot))
 
     def take(self):

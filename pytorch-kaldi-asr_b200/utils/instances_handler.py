@@ -1,7 +1,8 @@
 """Batch assembly -- the producer side of the hot path's input contract (reference U/instances_handler.py:118-139).
 
-Only `pad_to_longest` is on the path (it fixes layout and mask polarity: 1 = real, 0 = pad, trailing padding only);
-the reference's vocabulary/text helpers are data preparation and out of scope."""
+`pad_to_longest` is on the path (it fixes layout and mask polarity: 1 = real, 0 = pad, trailing padding only).  The
+label helpers `initialize_batch_loader` needs (`read_vocab`, `add_control_words`, `apply_vocab`; U/instances_handler.py:
+73-110) are here for the loader; vocabulary building and text preparation stay out of scope."""
 from __future__ import annotations
 
 import numpy as np
@@ -23,3 +24,37 @@ def pad_to_longest(instances):
         data[i, :n] = x
         mask[i, :n] = 1
     return data, mask
+
+
+def read_vocab(vocab_file):
+    """Symbol table 'word index' per line -> {word: index} (U/instances_handler.py:73-82)."""
+    word2idx = {}
+    with open(vocab_file, encoding='utf-8') as f:
+        for n, line in enumerate(f, 1):
+            fields = line.split()
+            if not fields:
+                continue
+            if len(fields) < 2:
+                raise ValueError('[ERROR] {} line {}: expected "word index"'.format(vocab_file, n))
+            word2idx[fields[0]] = int(fields[1])
+    return word2idx
+
+
+def add_control_words(instances_index):
+    """{key: [words]} -> {key: array([<s>, words..., </s>])}, in place like the reference (U/instances_handler.py:86-90)."""
+    for key, words in instances_index.items():
+        instances_index[key] = np.array([constants.BOS_WORD] + list(words) + [constants.EOS_WORD])
+    return instances_index
+
+
+def apply_vocab(instances, vocab_file, mode):
+    """mode 'word2idx': words -> int64 indices (UNK for unknown words); 'idx2word': the inverse (UNK_WORD for unknown
+    indices).  `vocab_file` may also be an already loaded {word: index} dict.  (U/instances_handler.py:94-110)"""
+    word2idx = vocab_file if isinstance(vocab_file, dict) else read_vocab(vocab_file)
+    if mode == 'word2idx':
+        return {key: np.array([word2idx.get(w, constants.UNK) for w in words], dtype=np.int64)
+                for key, words in instances.items()}
+    if mode == 'idx2word':
+        idx2word = {i: w for w, i in word2idx.items()}
+        return {key: [idx2word.get(int(i), constants.UNK_WORD) for i in idxs] for key, idxs in instances.items()}
+    raise ValueError('[ERROR] invalid mode string: {!r}'.format(mode))
