@@ -10,8 +10,11 @@ The reference scripts (L/train.py, L/decode.py, L/initialize_model.py) import th
 `import pytorch_kaldi_asr_b200.dropin` (before those lines) registers the B200 implementations under exactly these
 names, so the scripts run unchanged apart from that one import.  `utils.BatchLoader` (U/BatchLoader.py) resolves to
 the loader of this package, and -- only when the external `kaldi_io` package the reference depends on is not
-installed -- `kaldi_io` resolves to `utils/kaldi_ark.py` (`read_mat`, `read_mat_scp`, `read_mat_ark`).
+installed -- `kaldi_io` resolves to `utils/kaldi_ark.py` (`read_mat`, `read_mat_scp`, `read_mat_ark`).  `utils`
+submodules this package does not provide (`utils.get_gpu`, imported by L/train.py:18) keep resolving to the reference's
+`pytorch/utils` directory when it is on `sys.path`: that directory is appended to the `__path__` of our `utils`.
 """
+import os
 import sys
 
 from . import TDNN as _tdnn
@@ -33,6 +36,12 @@ def install(override_utils: bool = False):
         sys.modules.setdefault("utils.constants", _constants)
         sys.modules.setdefault("utils.instances_handler", _ih)
         sys.modules.setdefault("utils.BatchLoader", _batch_loader)
+        if sys.modules["utils"] is _utils:
+            own = [os.path.realpath(p) for p in _utils.__path__]
+            for entry in sys.path:
+                cand = os.path.join(entry or ".", "utils")
+                if os.path.isdir(cand) and os.path.realpath(cand) not in own and cand not in _utils.__path__:
+                    _utils.__path__.append(cand)
     if "kaldi_io" not in sys.modules:
         import importlib.util
         if importlib.util.find_spec("kaldi_io") is None:
