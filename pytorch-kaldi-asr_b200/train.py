@@ -342,3 +342,107 @@ class GraphedTrainStep:
         self.load(src, smask, tgt, tmask)
         self.graph.replay()
         return self.out
+
+
+# ------------------------------------------------------------------------------------------------ epoch driver
+def get_criterion(vocab_size):
+    """Kept for call-site compatibility (L/train.py:326-330): the loss kernel ignores PAD targets itself, `crit` is unused."""
+    weight = torch.ones(vocab_size)
+    weight[constants.PAD] = 0
+    return torch.nn.CrossEntropyLoss(weight, reduction='sum')
+
+
+def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_options, graphed=None):
+    """Epoch loop of L/train.py:217-272: train, evaluate 10 training batches / dev / test, checkpoint every
+    `opt.save_interval` epochs and every epoch of the last interval, finally write the best-on-dev model.
+    -> (best_accu, best_epoch).
+
+    Differences: checkpoints are state-dict files with optimiser / schedule / dropout state (checkpoint.py), so a run
+    can resume bit-exactly; the best model is a *snapshot* taken at its epoch (the reference keeps a reference to the
+    live module, L/train.py:243-245, and therefore saves the last epoch's weights under the best epoch's name).
+    Like the reference, every evaluation stops after `batch_eval` = 10 batches (L/train.py:127,209-212)."""
+    import time
+    from . import checkpoint as _ckpt
+    start_all, best_epoch, best_accu, best_state = time.time(), 0, 0.0, None
+    first = int(getattr(opt, 'start_epoch', 1))
+    for epoch in range(first, opt.epoch + 1):
+        print('[INFO] trainning epoch {}.'.format(epoch))
+        start = time.time()
+        _, train_accu = train_epoch(model, train_data, crit, mode='train', optimizer=optimizer, use_gpu=True,
+                                    seq_error_prob=getattr(opt, 'seq_error_prob', 0), graphed=graphed)
+        print('[INFO]-----(Training)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
+              .format(100 * train_accu, (time.time() - start) / 60))
+        start = time.time()
+        eval_batch_num = 10
+        _, accu = train_epoch(model, train_data, crit, mode='eval', batch_eval=eval_batch_num, use_gpu=True)
+        print('[INFO]-----(evaluating train set for {} batch)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
+              .format(eval_batch_num, 100 * accu, (time.time() - start) / 60))
+        start = time.time()
+        _, valid_accu = train_epoch(model, dev_data, crit, mode='eval', use_gpu=True)
+        print('[INFO]-----(evaluating dev set)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
+              .format(100 * valid_accu, (time.time() - start) / 60))
+        if valid_accu > best_accu:
+            best_accu, best_epoch = valid_accu, epoch
+            best_state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        start = time.time()
+        _, test_accu = train_epoch(model, test_data, crit, mode='eval', use_gpu=True)
+        print('[INFO]-----(evaluating test set)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
+              .format(100 * test_accu, (time.time() - start) / 60))
+        if epoch % opt.save_interval == 0 or opt.epoch - epoch < opt.save_interval:
+            model_name = opt.save_model_dir + '/epoch.{}.torch'.format(epoch)
+            _ckpt.save_checkpoint(model_name, model, model_options, epoch, train_options=opt, optimizer=optimizer)
+            print('[INFO] checkpoint of epoch {} is saved to {}'.format(epoch, model_name))
+    print('[INFO] trainning finish.\n\ttime consume: {:3.2f} minute\n\tbest valid accuracy: {:3.2f} %, on epoch {}'
+          .format((time.time() - start_all) / 60, 100 * best_accu, best_epoch))
+    if best_state is not None:
+        model_name = opt.save_model_dir + '/best.epoch{}.accu{:3.2f}.torch'.format(best_epoch, 100 * best_accu)
+        _ckpt.save_state(model_name, best_state, model, model_options, best_epoch, train_options=opt)
+        print('[INFO] best model is saved to {}'.format(model_name))
+    return best_accu, best_epoch
+
+
+def combine(opt, epoch, crit, data, num_model=20):
+    """Model averaging of L/train.py:284-322: running mean over the checkpoints of epochs `epoch`, `epoch-1`, ...
+    (`num_model` of them, missing files end the walk), evaluated on `data` after every addition; the best average is
+    written to `combined.accuXX.XX.torch`.  -> best accuracy.
+
+    The running mean lives on the GPU in the reference's arithmetic (checkpoint.running_average); the best average is a
+    snapshot (the reference's `best_model` aliases the live module, so it saves the last average whatever its score)."""
+    import math
+    import os
+    import time
+    from . import checkpoint as _ckpt
+    print('[PROCEDURE] combining model with model averaging...')
+    files = []
+    for i in range(epoch, epoch - num_model, -1):
+        name = opt.save_model_dir + '/epoch.{}.torch'.format(i)
+        if not os.path.exists(name):
+            break
+        files.append(name)
+    if not files:
+        raise ValueError('[ERROR] no checkpoint epoch.{}.torch under {}'.format(epoch, opt.save_model_dir))
+    first = _ckpt.load_checkpoint(files[0], device='cuda')
+    model, model_options = first['model'], first['model_options']
+    print('[INFO] model loaded')
+
+    def states():
+        yield {k: v.to('cuda') for k, v in first['state_dict'].items()}
+        for name in files[1:]:
+            yield {k: v.to('cuda') for k, v in _ckpt.read_checkpoint(name)['state_dict'].items()}
+
+    best_accu, best_state, best_n = -1.0, None, 0
+    for n, avg in _ckpt.running_average(states()):
+        print('[INFO] averaging {} models'.format(n))
+        model.load_state_dict(avg)
+        start = time.time()
+        test_loss, test_accu = train_epoch(model, data, crit, mode='eval', use_gpu=True)
+        print('[INFO]-----(evaluating combining set)----- ppl: {:7.3f}, accuracy: {:3.2f} %, elapse: {:3.2f} min'
+              .format(math.exp(min(test_loss, 100)), 100 * test_accu, (time.time() - start) / 60))
+        if test_accu > best_accu:
+            best_accu, best_n = test_accu, n
+            best_state = {k: v.detach().cpu().clone() for k, v in avg.items()}
+    print('[INFO] best combined model with accuracy: {:3.2f} %'.format(100 * best_accu))
+    model_name = opt.save_model_dir + '/combined.accu{:3.2f}.torch'.format(100 * best_accu)
+    _ckpt.save_state(model_name, best_state, model, model_options, first['epoch'], train_options=opt,
+                     extra=dict(averaged_models=best_n, averaged_from=files[:best_n]))
+    return best_accu

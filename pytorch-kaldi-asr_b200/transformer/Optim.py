@@ -20,7 +20,9 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, bf16_shadow=False):
         params = [p for p in params]
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        # weight_decay / amsgrad are fixed at torch.optim.Adam's defaults; they are listed so that this optimizer's
+        # state_dict() loads into a stock Adam (which reads both keys from every parameter group)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
         self._train = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
         if not self._train:
             raise ValueError("FusedAdam: no trainable parameters")
@@ -53,6 +55,68 @@ class FusedAdam(torch.optim.Optimizer):
         self.dev_state = torch.zeros(2, device=dev, dtype=torch.int64)        # {adam_t, n_current_steps}
         self.dev_lr = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.use_device_lr = False                                            # switched on by ScheduledOptim
+
+    # ---- state interchange: torch.optim.Adam's own layout, so checkpoints move between FusedAdam and stock Adam ----
+    def _param_index(self):
+        return {id(p): i for i, p in enumerate(q for g in self.param_groups for q in g["params"])}
+
+    def state_dict(self):
+        """{'state': {param index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} as torch.optim.Adam writes
+        it (per-parameter copies of the arena moments; empty before the first step), plus 'fused': the device-side
+        counters {adam_t, n_current_steps, lr}.  Synchronises the stream (checkpoint time only)."""
+        base = super().state_dict()
+        adam_t, n_sched = (int(v) for v in self.dev_state.tolist())
+        state = {}
+        if adam_t > 0:
+            index = self._param_index()
+            for p, off in zip(self._train, self._offsets):
+                sl = slice(off, off + p.numel())
+                state[index[id(p)]] = dict(step=torch.tensor(float(adam_t)),
+                                           exp_avg=self.exp_avg[sl].view(p.shape).clone(),
+                                           exp_avg_sq=self.exp_avg_sq[sl].view(p.shape).clone())
+        base["state"] = state
+        base["fused"] = dict(adam_t=adam_t, n_current_steps=n_sched, lr=float(self.dev_lr.item()))
+        return base
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != len(self.param_groups) or \
+                any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("FusedAdam.load_state_dict: parameter groups do not match this optimizer")
+        for mine, theirs in zip(self.param_groups, groups):
+            for key in ("lr", "betas", "eps"):
+                if key in theirs:
+                    mine[key] = tuple(theirs[key]) if key == "betas" else theirs[key]
+        index = self._param_index()
+        state = {int(k): v for k, v in state_dict.get("state", {}).items()}
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for p, off in zip(self._train, self._offsets):
+            entry = state.get(index[id(p)])
+            if entry is None:
+                continue
+            if tuple(entry["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("FusedAdam.load_state_dict: moment shape %s does not match parameter shape %s"
+                                 % (tuple(entry["exp_avg"].shape), tuple(p.shape)))
+            sl = slice(off, off + p.numel())
+            self.exp_avg[sl].view(p.shape).copy_(entry["exp_avg"])
+            self.exp_avg_sq[sl].view(p.shape).copy_(entry["exp_avg_sq"])
+            steps.add(int(float(entry["step"])))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam.load_state_dict: parameters with different step counts %s (one shared "
+                             "bias-correction step is kept for the whole arena)" % sorted(steps))
+        fused = state_dict.get("fused", {})
+        adam_t = int(fused.get("adam_t", steps.pop() if steps else 0))
+        self.dev_state.copy_(torch.tensor([adam_t, int(fused.get("n_current_steps", 0))], dtype=torch.int64))
+        self.dev_lr.fill_(float(fused.get("lr", self.param_groups[0]["lr"])))
+
+    @torch.no_grad()
+    def set_schedule_step(self, n_current_steps, lr):
+        """Device-side copy of ScheduledOptim's counter and current learning rate (checkpoint restore)."""
+        self.dev_state[1] = int(n_current_steps)
+        self.dev_lr.fill_(float(lr))
 
     def grad_view(self, p):
         i = next(k for k, q in enumerate(self._train) if q is p)

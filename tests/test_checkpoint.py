@@ -1,0 +1,83 @@
+"""CPU tests of checkpoints and model averaging against fixtures written by the REAL reference
+(tests/golden/make_checkpoint_golden.py): a whole-module pickle as L/initialize_model.py saves it, and the running
+averages of its own `scale_dict` / `add_dict`."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pytorch_kaldi_asr_b200 import checkpoint as ck
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REF_FILE = os.path.join(GOLDEN, "ref_checkpoint_tiny.torch")
+
+
+def golden_arrays():
+    g = np.load(os.path.join(GOLDEN, "checkpoint_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    return g, sd
+
+
+def perturbed(sd, i):          # same recipe as make_checkpoint_golden.py
+    out = {}
+    for j, (k, v) in enumerate(sd.items()):
+        noise = np.random.RandomState(1000 * i + j).randn(*v.shape).astype(np.float32)
+        out[k] = v + 0.05 * torch.from_numpy(noise).reshape(v.shape)
+    return out
+
+
+def test_reference_pickled_module_checkpoint_loads_into_this_package():
+    g, sd = golden_arrays()
+    raw = ck.read_checkpoint(REF_FILE)
+    assert raw["format"] == "reference-pickled-module" and raw["epoch"] == 0 and raw["optimizer"] is None
+    assert raw["model_options"]["src_dim"] == 4 and raw["model_options"]["tdnn_contexts"] == [[-1, 0, 1], [-3, 0, 3]]
+    assert set(raw["state_dict"]) == set(sd)
+    for k in sd:
+        assert torch.equal(raw["state_dict"][k], sd[k]), k
+    kw = ck.model_kwargs(raw["model_options"])
+    assert kw["n_src_dim"] == 4 and kw["n_tgt_vocab"] == 9 and kw["encoder_sub_sequence"] == (-100, 0)
+    assert kw["decoder_sub_sequence"] == (-3, 0) and kw["en_d_model"] == 16 and "read_vocab_file" not in kw
+    np.testing.assert_array_equal(ck.lda_from_state_dict(raw["state_dict"]), g["lda_mat"])
+    full = ck.load_checkpoint(REF_FILE)
+    model = full["model"]
+    assert type(model).__module__ == "pytorch_kaldi_asr_b200.transformer.Models"
+    assert hasattr(model, "dropout_state")                       # a properly constructed instance, not the unpickled shell
+    got = model.state_dict()
+    assert list(got) == list(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+
+
+def test_state_dict_checkpoint_round_trip_is_plain_data(tmp_path):
+    _, sd = golden_arrays()
+    model = ck.load_checkpoint(REF_FILE)["model"]
+    path = str(tmp_path / "epoch.3.torch")
+    opts = ck.read_checkpoint(REF_FILE)["model_options"]
+    ck.save_checkpoint(path, model, argparse.Namespace(**opts), 3, train_options=argparse.Namespace(epoch=50, batch_size=32),
+                       extra=dict(note="x"))
+    assert os.listdir(str(tmp_path)) == ["epoch.3.torch"]       # the temporary file was renamed into place
+    plain = torch.load(path, map_location="cpu", weights_only=True)      # no pickled classes inside
+    assert plain["format"] == ck.FORMAT and plain["epoch"] == 3 and plain["train_options"] == dict(epoch=50, batch_size=32)
+    assert plain["model_options"]["seed"] == 0 and plain["model_options"]["encoder_type"] == "tdnn"
+    again = ck.load_checkpoint(path)
+    assert again["extra"] == dict(note="x") and again["optimizer"] is None
+    got = again["model"].state_dict()
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.raises(ValueError):
+        ck.model_kwargs(dict(en_d_model=16))
+    torch.save([1, 2, 3], str(tmp_path / "junk.torch"))
+    with pytest.raises(ValueError):
+        ck.read_checkpoint(str(tmp_path / "junk.torch"))
+
+
+def test_running_average_equals_the_reference_combine_arithmetic():
+    g, sd = golden_arrays()
+    seen = 0
+    for n, avg in ck.running_average(perturbed(sd, i) for i in range(4)):
+        for k in sd:
+            want = torch.from_numpy(g["avg%d.%s" % (n, k)])
+            assert torch.equal(avg[k], want), (n, k)             # same ops in the same order: bit-exact
+        seen = n
+    assert seen == 4
+    with pytest.raises(ValueError):
+        list(ck.running_average([sd, {k: v for k, v in list(sd.items())[:-1]}]))
