@@ -170,14 +170,17 @@ class _Prefetcher:
 
 
 def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_eval=10, use_gpu=False, seq_error_prob=0,
-                smoothing=False, graphed: Optional["GraphedTrainStep"] = None, sync_every_step: bool = False):
+                smoothing=False, graphed: Optional["GraphedTrainStep"] = None, sync_every_step: bool = False,
+                grad_sync=None):
     """One pass over `batch_loader` (L/train.py:127-214).  Returns (loss per word, token accuracy).
 
     Differences from the reference, all behaviour-preserving: the dead `use_seq_error` branches are not carried; the
     label-smoothing switch the reference hard-wires to False (L/train.py:193) is a keyword (default False); the three
     running totals stay on the device and are read back once per epoch (`sync_every_step=True` reads them back after
-    every step like the reference does); host->device copies of batch i+1 overlap step i.  This path has no CPU mode: the
-    model must be on a CUDA device (`use_gpu` is accepted for signature compatibility)."""
+    every step like the reference does); host->device copies of batch i+1 overlap step i.  `grad_sync` (data parallel:
+    `parallel.GradAllReduce(...).finish`) is called between backward and the optimiser step of the eager path; a
+    `graphed` step carries its own.  This path has no CPU mode: the model must be on a CUDA device (`use_gpu` is
+    accepted for signature compatibility)."""
     if mode == 'train':
         model.train()
         batch_loader.mode = 'drop'
@@ -248,6 +251,8 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
         loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), smoothing)
         if mode == 'train':
             loss.backward()
+            if grad_sync is not None:
+                grad_sync()
             optimizer.step()
             optimizer.update_learning_rate()
         feed.release()
@@ -352,7 +357,8 @@ def get_criterion(vocab_size):
     return torch.nn.CrossEntropyLoss(weight, reduction='sum')
 
 
-def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_options, graphed=None):
+def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_options, graphed=None, grad_sync=None,
+          writer=True):
     """Epoch loop of L/train.py:217-272: train, evaluate 10 training batches / dev / test, checkpoint every
     `opt.save_interval` epochs and every epoch of the last interval, finally write the best-on-dev model.
     -> (best_accu, best_epoch).
@@ -360,6 +366,7 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
     Differences: checkpoints are state-dict files with optimiser / schedule / dropout state (checkpoint.py), so a run
     can resume bit-exactly; the best model is a *snapshot* taken at its epoch (the reference keeps a reference to the
     live module, L/train.py:243-245, and therefore saves the last epoch's weights under the best epoch's name).
+    Data parallel: every rank calls this with its shard of `train_data` and `grad_sync`; `writer` is True on one rank.
     Like the reference, every evaluation stops after `batch_eval` = 10 batches (L/train.py:127,209-212)."""
     import time
     from . import checkpoint as _ckpt
@@ -369,7 +376,7 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
         print('[INFO] trainning epoch {}.'.format(epoch))
         start = time.time()
         _, train_accu = train_epoch(model, train_data, crit, mode='train', optimizer=optimizer, use_gpu=True,
-                                    seq_error_prob=getattr(opt, 'seq_error_prob', 0), graphed=graphed)
+                                    seq_error_prob=getattr(opt, 'seq_error_prob', 0), graphed=graphed, grad_sync=grad_sync)
         print('[INFO]-----(Training)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
               .format(100 * train_accu, (time.time() - start) / 60))
         start = time.time()
@@ -388,13 +395,13 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
         _, test_accu = train_epoch(model, test_data, crit, mode='eval', use_gpu=True)
         print('[INFO]-----(evaluating test set)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
               .format(100 * test_accu, (time.time() - start) / 60))
-        if epoch % opt.save_interval == 0 or opt.epoch - epoch < opt.save_interval:
+        if writer and (epoch % opt.save_interval == 0 or opt.epoch - epoch < opt.save_interval):
             model_name = opt.save_model_dir + '/epoch.{}.torch'.format(epoch)
             _ckpt.save_checkpoint(model_name, model, model_options, epoch, train_options=opt, optimizer=optimizer)
             print('[INFO] checkpoint of epoch {} is saved to {}'.format(epoch, model_name))
     print('[INFO] trainning finish.\n\ttime consume: {:3.2f} minute\n\tbest valid accuracy: {:3.2f} %, on epoch {}'
           .format((time.time() - start_all) / 60, 100 * best_accu, best_epoch))
-    if best_state is not None:
+    if best_state is not None and writer:
         model_name = opt.save_model_dir + '/best.epoch{}.accu{:3.2f}.torch'.format(best_epoch, 100 * best_accu)
         _ckpt.save_state(model_name, best_state, model, model_options, best_epoch, train_options=opt)
         print('[INFO] best model is saved to {}'.format(model_name))
