@@ -1,6 +1,6 @@
 """Decoding entry point -- flags and flow of L/decode.py:110-161: load a model file, beam-search a data directory, write
 the n-best result file.  Under torchrun every rank decodes its share of the batches (no collective) into
-`<save_result_file>.<rank>`; rank 0 concatenates them in batch order at the end."""
+`<save_result_file>.<rank>`; rank 0 concatenates them (rank by rank) at the end -- consumers group lines by key."""
 import argparse
 import os
 
@@ -16,6 +16,9 @@ def build_parser():
     parser.add_argument('-beam_size', type=int, default=20)
     parser.add_argument('-nbest', type=int, default=10)
     parser.add_argument('-use_gpu', action='store_true')
+    # beyond the reference.  The TDNN encoder does not mask padding (its output on the last 16 real frames depends on
+    # how many pad frames follow), so the default keeps the reference loader's whole-set padding and its exact results.
+    parser.add_argument('-pad_to', choices=('dataset', 'batch'), default='dataset')
     return parser
 
 
@@ -31,7 +34,7 @@ def main(argv=None):
     model, model_options = loaded['model'], loaded['model_options']
     print('[INFO] loading model with parameter: {}'.format(model_options))
     decode_data = T.initialize_batch_loader(opt.read_data_dir + '/feats.scp', opt.read_data_dir + '/text',
-                                            opt.read_vocab_file, opt.batch_size, mode='all', pad_to='batch',
+                                            opt.read_vocab_file, opt.batch_size, mode='all', pad_to=opt.pad_to,
                                             seed=0 if world > 1 else None, shard=(rank, world))
     print('[INFO] batch loader is initialized')
     target = opt.save_result_file if world == 1 else '{}.{}'.format(opt.save_result_file, rank)
@@ -49,6 +52,8 @@ def main(argv=None):
                     with open(part, encoding='utf-8') as f:
                         out.write(f.read())
                     os.remove(part)
+        dist.barrier()
+        dist.destroy_process_group()
     return n
 
 

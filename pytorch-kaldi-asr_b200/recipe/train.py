@@ -79,12 +79,15 @@ def main(argv=None):
     os.makedirs(opt.save_model_dir, exist_ok=True)
     print('[PROCEDURE] trainning start...')
     best_accu, best_epoch = T.train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_options,
-                                    graphed=graphed, grad_sync=grad_sync, writer=(rank == 0))
+                                    graphed=graphed, grad_sync=grad_sync, writer=(rank == 0),
+                                    stats_reduce=parallel.all_reduce_stats if world > 1 else None)
     if rank == 0:
         print('[PROCEDURE] combining start on best epoch {}'.format(best_epoch))
         best_accu = T.combine(opt, best_epoch, crit, dev_data, 30 if opt.epoch > 30 else opt.epoch)
     if world > 1:
         torch.distributed.barrier()
+        torch.cuda.synchronize()
+        torch.distributed.destroy_process_group()
     return best_accu
 
 

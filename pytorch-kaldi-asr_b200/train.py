@@ -171,7 +171,7 @@ class _Prefetcher:
 
 def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_eval=10, use_gpu=False, seq_error_prob=0,
                 smoothing=False, graphed: Optional["GraphedTrainStep"] = None, sync_every_step: bool = False,
-                grad_sync=None):
+                grad_sync=None, stats_reduce=None):
     """One pass over `batch_loader` (L/train.py:127-214).  Returns (loss per word, token accuracy).
 
     Differences from the reference, all behaviour-preserving: the dead `use_seq_error` branches are not carried; the
@@ -179,7 +179,8 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
     running totals stay on the device and are read back once per epoch (`sync_every_step=True` reads them back after
     every step like the reference does); host->device copies of batch i+1 overlap step i.  `grad_sync` (data parallel:
     `parallel.GradAllReduce(...).finish`) is called between backward and the optimiser step of the eager path; a
-    `graphed` step carries its own.  This path has no CPU mode: the model must be on a CUDA device (`use_gpu` is
+    `graphed` step carries its own; `stats_reduce` (`parallel.all_reduce_stats`) sums the epoch's three totals over the
+    ranks before the ratios are taken (L/train.py:203-214 on the global batch).  This path has no CPU mode: the model must be on a CUDA device (`use_gpu` is
     accepted for signature compatibility)."""
     if mode == 'train':
         model.train()
@@ -267,6 +268,9 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
             if seen == batch_eval:
                 break
     flush()
+    if stats_reduce is not None:
+        totals = stats_reduce(totals + torch.tensor(host_totals, dtype=torch.float64, device=device))
+        host_totals = [0.0, 0.0, 0.0]
     loss_sum, n_correct, n_words = [a + b for a, b in zip(totals.tolist(), host_totals)]
     return loss_sum / int(n_words), n_correct / int(n_words)
 
@@ -358,7 +362,7 @@ def get_criterion(vocab_size):
 
 
 def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_options, graphed=None, grad_sync=None,
-          writer=True):
+          writer=True, stats_reduce=None):
     """Epoch loop of L/train.py:217-272: train, evaluate 10 training batches / dev / test, checkpoint every
     `opt.save_interval` epochs and every epoch of the last interval, finally write the best-on-dev model.
     -> (best_accu, best_epoch).
@@ -376,7 +380,8 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
         print('[INFO] trainning epoch {}.'.format(epoch))
         start = time.time()
         _, train_accu = train_epoch(model, train_data, crit, mode='train', optimizer=optimizer, use_gpu=True,
-                                    seq_error_prob=getattr(opt, 'seq_error_prob', 0), graphed=graphed, grad_sync=grad_sync)
+                                    seq_error_prob=getattr(opt, 'seq_error_prob', 0), graphed=graphed, grad_sync=grad_sync,
+                                    stats_reduce=stats_reduce)
         print('[INFO]-----(Training)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
               .format(100 * train_accu, (time.time() - start) / 60))
         start = time.time()
