@@ -247,7 +247,9 @@ def hbm_probe():
     pk_ = peaks()
     gbs = 3.0 * rows * D * 4 / sec / 1e9
     return {"kernel": "add_ln_fwd_kernel", "achieved": gbs, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk_["hbm_gbs"],
-            "bytes_per_launch": 3 * rows * D * 4}
+            "bytes_per_launch": 3 * rows * D * 4,
+            "note": "2 reads : 1 write per element; the peak is the measured 1:1 copy figure, which a read-heavy kernel "
+                    "can exceed by a few percent (ncu: 98 % of it in DRAM throughput, profiles/r01_kernel_evidence.md)"}
 
 
 def cfg5_bench(B=4, band=(-100, 0), steps=5, warmup=3, profile=False):
