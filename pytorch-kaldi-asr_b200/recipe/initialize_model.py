@@ -1,68 +1,61 @@
-"""Build the initial model file from Kaldi data -- flags and behaviour of L/initialize_model.py:23-99: feature dimension
-from the first scp entry, vocabulary size from the vocab file, frozen LDA from `lda.mat`, the recipe's fixed TDNN
-contexts; written as an epoch-0 state-dict checkpoint (checkpoint.py)."""
+"""Build the initial model file from Kaldi data.  Same command line as L/initialize_model.py:23-46; same behaviour:
+feature dimension from the first scp entry, vocabulary size from the vocab file, frozen LDA from `lda.mat`, the
+recipe's fixed TDNN contexts (:48-53).  The result is an epoch-0 state-dict checkpoint (checkpoint.py)."""
 import argparse
 
-TDNN_CONTEXTS = [[-1, 0, 1], [-1, 0, 1], [-3, 0, 3], [-3, 0, 3], [-3, 0, 3], [-3, 0, 3]]      # L/initialize_model.py:48-53
+TDNN_CONTEXTS = ((-1, 0, 1),) * 2 + ((-3, 0, 3),) * 4
+REQUIRED = object()
+
+# flag, type, default -- the reference's names and defaults; `init_seed` is new (seed of the weight initialisation)
+FLAGS = (
+    ('read_feats_scp_file', str, REQUIRED), ('lda_mat_file', str, REQUIRED), ('read_vocab_file', str, REQUIRED),
+    ('encoder_max_len', int, REQUIRED), ('decoder_max_len', int, REQUIRED), ('src_fold', int, 1),
+    ('encoder_sub_sequence', str, '(-100,0)'), ('decoder_sub_sequence', str, '(-20,0)'),
+    ('en_layers', int, 2), ('de_layers', int, 2), ('n_head', int, 3), ('en_d_model', int, 256), ('de_d_model', int, 128),
+    ('d_k', int, 64), ('d_v', int, 64), ('en_dropout', float, 0.2), ('de_dropout', float, 0.2),
+    ('save_model_file', str, REQUIRED), ('init_seed', int, None),
+)
 
 
-def str2tuple(string):
-    """'(-100,0)' -> (-100, 0)   (L/initialize_model.py:13-21)"""
-    body = string.strip()
-    if not (body.startswith('(') and body.endswith(')')):
-        raise ValueError('[ERROR] invalid sub-sequence string!')
-    parts = body[1:-1].split(',')
-    if len(parts) != 2:
-        raise ValueError('[ERROR] invalid sub-sequence string!')
-    return int(parts[0]), int(parts[1])
+def str2tuple(text):
+    """'(-100,0)' -> (-100, 0)"""
+    try:
+        lo, hi = text.strip().lstrip('(').rstrip(')').split(',')
+        return int(lo), int(hi)
+    except ValueError:
+        raise ValueError('[ERROR] invalid sub-sequence string!') from None
 
 
 def build_parser():
-    parser = argparse.ArgumentParser()
-    parser.add_argument('-read_feats_scp_file', required=True)
-    parser.add_argument('-lda_mat_file', required=True)
-    parser.add_argument('-read_vocab_file', required=True)
-    parser.add_argument('-encoder_max_len', type=int, required=True)
-    parser.add_argument('-decoder_max_len', type=int, required=True)
-    parser.add_argument('-src_fold', type=int, default=1)
-    parser.add_argument('-encoder_sub_sequence', default='(-100,0)')
-    parser.add_argument('-decoder_sub_sequence', default='(-20,0)')
-    parser.add_argument('-en_layers', type=int, default=2)
-    parser.add_argument('-de_layers', type=int, default=2)
-    parser.add_argument('-n_head', type=int, default=3)
-    parser.add_argument('-en_d_model', type=int, default=256)
-    parser.add_argument('-de_d_model', type=int, default=128)
-    parser.add_argument('-d_k', type=int, default=64)
-    parser.add_argument('-d_v', type=int, default=64)
-    parser.add_argument('-en_dropout', type=float, default=0.2)
-    parser.add_argument('-de_dropout', type=float, default=0.2)
-    parser.add_argument('-save_model_file', required=True)
-    parser.add_argument('-init_seed', type=int, default=None, help='torch seed for the weight initialisation')
+    parser = argparse.ArgumentParser(description=__doc__)
+    for name, kind, default in FLAGS:
+        if default is REQUIRED:
+            parser.add_argument('-' + name, type=kind, required=True)
+        else:
+            parser.add_argument('-' + name, type=kind, default=default)
     return parser
 
 
 def main(argv=None):
     import torch
     from .. import checkpoint
+    from ..transformer.Models import Transformer
     from ..utils import instances_handler, kaldi_ark
     opt = build_parser().parse_args(argv)
-    opt.tdnn_contexts = [list(c) for c in TDNN_CONTEXTS]
-    opt.encoder_sub_sequence = str2tuple(opt.encoder_sub_sequence)
-    opt.decoder_sub_sequence = str2tuple(opt.decoder_sub_sequence)
-    for _, matrix in kaldi_ark.read_mat_scp(opt.read_feats_scp_file):
-        opt.src_dim = int(matrix.shape[1])
-        break
-    else:
+    opt.tdnn_contexts = [list(ctx) for ctx in TDNN_CONTEXTS]
+    opt.encoder_sub_sequence, opt.decoder_sub_sequence = (str2tuple(s) for s in (opt.encoder_sub_sequence,
+                                                                                 opt.decoder_sub_sequence))
+    first = next(iter(kaldi_ark.read_mat_scp(opt.read_feats_scp_file)), None)
+    if first is None:
         raise ValueError('[ERROR] {} lists no utterance'.format(opt.read_feats_scp_file))
-    print('[INFO] get feature of dimension {} from {}.'.format(opt.src_dim, opt.read_feats_scp_file))
+    opt.src_dim = int(first[1].shape[1])
     opt.tgt_vocab_dim = len(instances_handler.read_vocab(opt.read_vocab_file))
-    print('[INFO] get label of dimension {} from {}.'.format(opt.tgt_vocab_dim, opt.read_vocab_file))
-    print('[INFO] model will initialized with add_argument:\n\t{}.'.format(opt))
-    lda_mat = kaldi_ark.read_mat(opt.lda_mat_file)
+    print('[INFO] feature dimension {} ({}), label dimension {} ({}).'.format(
+        opt.src_dim, opt.read_feats_scp_file, opt.tgt_vocab_dim, opt.read_vocab_file))
+    print('[INFO] model options:\n\t{}.'.format(opt))
     if opt.init_seed is not None:
         torch.manual_seed(opt.init_seed)
-    from ..transformer.Models import Transformer
-    model = Transformer(lda_mat=lda_mat, **checkpoint.model_kwargs(opt))
+    model = Transformer(lda_mat=kaldi_ark.read_mat(opt.lda_mat_file), **checkpoint.model_kwargs(opt))
     checkpoint.save_checkpoint(opt.save_model_file, model, opt, 0)
     print('[INFO] initialized model is saved to {}.'.format(opt.save_model_file))
     return opt
