@@ -407,7 +407,13 @@ def run_b200(args):
                                 for x, dt in zip(b[1:], (torch.float32, torch.uint8, torch.int64, torch.uint8)))
                 for b in pool]
     n_buckets = int(os.environ.get("PKA_BUCKETS", "3"))
-    sync = parallel.GradAllReduce(opt.optimizer, n_buckets=n_buckets, backend=os.environ.get("PKA_ALLREDUCE", "nccl")) if world > 1 else None
+    dp_backend = os.environ.get("PKA_ALLREDUCE", "nccl")
+    if world > 1 and dp_backend == "peer":
+        # one kernel per rank: gradient reduce-scatter + Adam on the shard + parameter all-gather over peer memory
+        opt.optimizer.enable_peer_step()
+        sync = None
+    else:
+        sync = parallel.GradAllReduce(opt.optimizer, n_buckets=n_buckets, backend=dp_backend) if world > 1 else None
     launches0 = _lib.launch_count()
     graphed, graph_note = None, "eager"
     if not args.no_graph:
@@ -522,6 +528,7 @@ def run_b200(args):
         "config": {"workload": "timit_example_model_train_step_B32 (BASELINE configs[1])", "global_batch": B * world,
                    "batch_per_gpu": B, "padded_T": int(b0[1].shape[1]), "padded_L": int(b0[3].shape[1] - 1),
                    "dropout": 0.35, "parallelism": "dp%d" % world, "execution": graph_note,
+                   "gradient_exchange": "none (1 GPU)" if world == 1 else dp_backend,
                    "l2": "no flush: %d distinct batches rotate and one step's activation working set (~0.5 GB) exceeds the 126 MB L2" % n_pool},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                 "ms_per_step": ms_e2e / args.steps, "api": "train_epoch(model, loader_of_K_pinned_batches, None, 'train', optimizer, graphed=..., sync_every_step=True)"},

@@ -233,6 +233,26 @@ int pka_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr_host, int64_t* state, float beta1, float beta2, float eps, void* bf16_shadow,
                   void* stream);
 int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream);
+
+/* ---- data-parallel optimiser step over peer memory (NVLink / NVSwitch) ------------------------------------------
+ * replaces, for W ranks: {all-reduce SUM of the gradient arena (the new exchange step of SURVEY.md 8e), pka_adam_step}
+ * by ONE kernel per rank: gradient reduce-scatter (multimem.ld_reduce through the switch when multicast addresses
+ * are given, W peer loads in rank order otherwise), Adam on the rank's 1/W shard of (param, exp_avg, exp_avg_sq),
+ * parameter all-gather (multimem.st / W peer stores), bracketed by two per-CTA flag handshakes with the peers.
+ *   param_ptrs / grad_ptrs : HOST arrays of W device addresses -- the symmetric parameter / gradient arena as mapped
+ *                            for rank 0..W-1 (entry `rank` is the local one); n floats each, n % (4*W) == 0
+ *   param_mc / grad_mc     : NVSwitch multicast addresses of the two arenas, or 0 / 0
+ *   flag_ptrs_dev          : DEVICE array of W device addresses of the ranks' flag arrays, each
+ *                            uint32[2 * pka_dp_adam_grid(n, W, max_ctas) * W], zero before the first call
+ *   exp_avg / exp_avg_sq   : local, n floats; only the rank's shard [rank*n/W, (rank+1)*n/W) is read and written
+ *   state, lr_dev, lr_host, beta1, beta2, eps: as pka_adam_step (adam_t is advanced on every rank)
+ * All ranks must call it with the same n, W and max_ctas, once per step, in the same order relative to each other.
+ * CUDA-graph capturable; the grid (<= 148 CTAs) has to be co-resident with whatever else runs on the device. */
+int pka_dp_adam_grid(int64_t n, int world, int max_ctas);
+int pka_dp_adam_step(const uint64_t* param_ptrs, const uint64_t* grad_ptrs, uint64_t param_mc, uint64_t grad_mc,
+                     const uint64_t* flag_ptrs_dev, int rank, int world, int max_ctas, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, const float* lr_dev, float lr_host, int64_t* state, float beta1, float beta2, float eps,
+                     void* stream);
 int pka_counter_inc(uint64_t* counter, void* stream);
 
 /* ---- (e) beam-search decoding ------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@ def build_parser():
     parser.add_argument('-graphed', action='store_true', help='replay the whole step as one CUDA graph (fixed batch shape)')
     parser.add_argument('-shuffle_seed', type=int, default=None, help='seed of the epoch shuffles (required for >1 GPU)')
     parser.add_argument('-resume', action='store_true', help='continue from the optimiser state in -load_model_file')
+    parser.add_argument('-dp_backend', choices=('nccl', 'peer'), default='nccl',
+                        help='>1 GPU: NCCL all-reduce + Adam, or the fused peer-memory reduce-scatter/Adam/all-gather kernel')
     return parser
 
 
@@ -61,7 +63,11 @@ def main(argv=None):
             raise ValueError('[ERROR] -resume: {} holds no optimiser state'.format(opt.load_model_file))
         checkpoint.restore_optimizer(optimizer, loaded['optimizer'], model)
         opt.start_epoch = int(loaded['epoch']) + 1
-    grad_sync = parallel.GradAllReduce(optimizer.optimizer).finish if world > 1 else None
+    grad_sync = None
+    if world > 1 and opt.dp_backend == 'peer':
+        optimizer.optimizer.enable_peer_step()
+    elif world > 1:
+        grad_sync = parallel.GradAllReduce(optimizer.optimizer).finish
 
     def loader(directory, **kw):
         return T.initialize_batch_loader(directory + '/feats.scp', directory + '/text', opt.read_vocab_file, opt.batch_size, **kw)

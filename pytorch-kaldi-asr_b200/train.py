@@ -400,7 +400,11 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
         _, test_accu = train_epoch(model, test_data, crit, mode='eval', use_gpu=True)
         print('[INFO]-----(evaluating test set)----- accuracy: {:3.2f} %, elapse: {:3.2f} min'
               .format(100 * test_accu, (time.time() - start) / 60))
-        if writer and (epoch % opt.save_interval == 0 or opt.epoch - epoch < opt.save_interval):
+        due = epoch % opt.save_interval == 0 or opt.epoch - epoch < opt.save_interval
+        inner = getattr(optimizer, 'optimizer', optimizer)
+        if due and getattr(inner, '_peer', None) is not None:
+            inner.sync_moments()                      # peer mode shards the Adam moments: gather them (all ranks)
+        if writer and due:
             model_name = opt.save_model_dir + '/epoch.{}.torch'.format(epoch)
             _ckpt.save_checkpoint(model_name, model, model_options, epoch, train_options=opt, optimizer=optimizer)
             print('[INFO] checkpoint of epoch {} is saved to {}'.format(epoch, model_name))

@@ -55,6 +55,89 @@ class FusedAdam(torch.optim.Optimizer):
         self.dev_state = torch.zeros(2, device=dev, dtype=torch.int64)        # {adam_t, n_current_steps}
         self.dev_lr = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.use_device_lr = False                                            # switched on by ScheduledOptim
+        self._peer = None                                                     # set by enable_peer_step()
+
+    # ---- data parallel: gradient reduce-scatter + Adam + parameter all-gather in one kernel over peer memory ----
+    def enable_peer_step(self, group=None, max_ctas: int = 32, multicast=None):
+        """Move the parameter and gradient arenas into NVLink symmetric memory (the same allocation mapped on every
+        rank of `group`) and make `step()` one `pka_dp_adam_step` launch per rank: the gradients of all ranks are summed
+        while being read (through the switch when NVLS multicast is available), this rank updates its 1/W shard and
+        writes the new parameters to every rank.  No separate all-reduce: do not combine with `GradAllReduce`.
+        Call on every rank, after construction and before `GraphedTrainStep` captures the step.  `multicast=False`
+        (or PKA_DP_MULTICAST=0) forces the peer-pointer path, whose summation order is fixed (bit-reproducible).
+        Adam moments then live sharded: call `sync_moments()` on every rank before `state_dict()`."""
+        import os
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from .. import ops as _ops
+        if self.flat_shadow is not None:
+            raise RuntimeError("enable_peer_step: the bf16 shadow arena is not supported in peer mode")
+        pg = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        dev = self.flat_param.device
+        quantum = 4 * world
+        n = (self.numel + quantum - 1) // quantum * quantum
+
+        def regrow(old, symmetric):
+            new = symm_mem.empty(n, dtype=torch.float32, device=dev) if symmetric else \
+                torch.empty(n, dtype=torch.float32, device=dev)
+            new.zero_()
+            new[:old.numel()].copy_(old)
+            return new
+
+        with torch.no_grad():
+            new_param, new_grad = regrow(self.flat_param, True), regrow(self.flat_grad, True)
+            for p, off in zip(self._train, self._offsets):
+                old_slot = self.flat_grad[off:off + p.numel()]
+                keeps_view = p.grad is not None and p.grad.data_ptr() == old_slot.data_ptr()
+                p.data = new_param[off:off + p.numel()].view(p.shape)
+                if keeps_view:
+                    p.grad = new_grad[off:off + p.numel()].view(p.shape)
+            self.exp_avg, self.exp_avg_sq = regrow(self.exp_avg, False), regrow(self.exp_avg_sq, False)
+            self.flat_param, self.flat_grad, self.numel = new_param, new_grad, n
+        _ops.register_grad_slots(self)                                        # the parameters moved
+        h_param, h_grad = symm_mem.rendezvous(new_param, pg), symm_mem.rendezvous(new_grad, pg)
+        grid = int(L.lib().pka_dp_adam_grid(C.c_int64(n), world, max_ctas))
+        flags = symm_mem.empty(2 * grid * world, dtype=torch.int32, device=dev)
+        flags.zero_()
+        h_flags = symm_mem.rendezvous(flags, pg)
+        if multicast is None:
+            multicast = os.environ.get("PKA_DP_MULTICAST", "1") != "0"
+
+        def addresses(handle, tensor):
+            """Peer addresses and multicast address of `tensor` (the handle describes the allocation it lives in)."""
+            off = tensor.data_ptr() - int(handle.buffer_ptrs[rank])    # position inside the symmetric allocation
+            if off < 0 or off + tensor.numel() * tensor.element_size() > int(handle.buffer_size):
+                raise RuntimeError("enable_peer_step: symmetric-memory handle does not describe this tensor "
+                                   "(local address %#x, allocation at %#x + %d bytes)"
+                                   % (tensor.data_ptr(), int(handle.buffer_ptrs[rank]), int(handle.buffer_size)))
+            peers = [int(a) + off for a in handle.buffer_ptrs]
+            mc = int(getattr(handle, "multicast_ptr", 0) or 0)
+            return peers, (mc + off if (mc and multicast) else 0)
+
+        param_peers, mc_param = addresses(h_param, new_param)
+        grad_peers, mc_grad = addresses(h_grad, new_grad)
+        flag_peers, _ = addresses(h_flags, flags)
+        if not (mc_param and mc_grad):
+            mc_param = mc_grad = 0
+        self._peer = dict(rank=rank, world=world, max_ctas=int(max_ctas), group=pg, handles=(h_param, h_grad, h_flags),
+                          flags=flags, param_ptrs=(C.c_uint64 * world)(*param_peers),
+                          grad_ptrs=(C.c_uint64 * world)(*grad_peers), param_mc=mc_param, grad_mc=mc_grad,
+                          flag_ptrs_dev=torch.tensor(flag_peers, dtype=torch.int64, device=dev))
+        torch.cuda.synchronize(dev)
+        dist.barrier(pg)                                                      # every rank's flags are zero before any launch
+        return self
+
+    @torch.no_grad()
+    def sync_moments(self):
+        """Peer mode keeps each rank's Adam moments valid only on its shard; gather them (collective: all ranks)."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+        pr = self._peer
+        for arena in (self.exp_avg, self.exp_avg_sq):
+            shard = arena.view(pr["world"], -1)[pr["rank"]].clone()
+            dist.all_gather_into_tensor(arena, shard, group=pr["group"])
 
     # ---- state interchange: torch.optim.Adam's own layout, so checkpoints move between FusedAdam and stock Adam ----
     def _param_index(self):
@@ -158,6 +241,15 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         b1, b2 = g["betas"]
         lr_dev = L.ptr(self.dev_lr) if self.use_device_lr else C.c_void_p(0)
+        if self._peer is not None:
+            pr = self._peer
+            L.check(L.lib().pka_dp_adam_step(pr["param_ptrs"], pr["grad_ptrs"], C.c_uint64(pr["param_mc"]),
+                                             C.c_uint64(pr["grad_mc"]), L.ptr(pr["flag_ptrs_dev"]), pr["rank"], pr["world"],
+                                             pr["max_ctas"], L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                             C.c_int64(self.numel), lr_dev, C.c_float(g["lr"]), L.ptr(self.dev_state),
+                                             C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]), L.stream_ptr()),
+                    "dp_adam_step")
+            return
         L.check(L.lib().pka_adam_step(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg),
                                       L.ptr(self.exp_avg_sq), C.c_int64(self.numel), lr_dev, C.c_float(g["lr"]),
                                       L.ptr(self.dev_state), C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]),
