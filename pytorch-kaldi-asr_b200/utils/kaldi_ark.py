@@ -29,6 +29,7 @@ import mmap
 import os
 import re
 import struct
+import threading
 from collections import OrderedDict
 from typing import Iterator, Optional, Tuple
 
@@ -161,9 +162,14 @@ class ArkReader:
 
     def __init__(self, max_open: int = 16):
         self.max_open = max_open
+        self._lock = threading.Lock()          # loaders read from a background thread (BatchLoader read_ahead)
         self._maps: "OrderedDict[str, tuple]" = OrderedDict()          # path -> (file, mmap, (mtime, size, inode))
 
     def _map(self, path: str):
+        with self._lock:
+            return self._map_locked(path)
+
+    def _map_locked(self, path: str):
         st = os.stat(path)
         stamp = (st.st_mtime_ns, st.st_size, st.st_ino)
         hit = self._maps.get(path)
@@ -187,10 +193,11 @@ class ArkReader:
 
     def read_mat(self, rxfilename: str) -> np.ndarray:
         path, offset, rows, cols = _split_rxfilename(rxfilename)
-        mm = self._map(path)
-        if offset >= len(mm):
-            raise KaldiFormatError("offset %d past the end of %s" % (offset, path))
-        mat, _ = _decode_object(mm, offset, len(mm))
+        with self._lock:                       # mapping, possible eviction of another archive and the copy out of it
+            mm = self._map_locked(path)
+            if offset >= len(mm):
+                raise KaldiFormatError("offset %d past the end of %s" % (offset, path))
+            mat, _ = _decode_object(mm, offset, len(mm))
         return _apply_range(mat, rows, cols) if (rows or cols) else mat
 
     def iter_ark(self, path: str) -> Iterator[Tuple[str, np.ndarray]]:
