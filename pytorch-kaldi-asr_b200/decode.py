@@ -266,19 +266,3 @@ def translate_batch(model, batch, opt, model_options=None):
     bd.reset(enc_output, fmask)
     bd.run()
     return bd.results(opt.nbest)
-
-
-def smoke_check(model, sd, cfg, batch):
-    """Used by __graft_entry__.smoke(): tiny beam search on cuda:0 compared with the CPU oracle (tokens exact)."""
-    import types
-    from oracle import beam_decode as obd
-    opt = types.SimpleNamespace(use_gpu=True, beam_size=4, max_token_seq_len=10, nbest=2, use_graph=True)
-    hyps, weights = translate_batch(model, batch, opt, None)
-    ref_h, ref_w, lats, _ = obd.translate_batch(sd, cfg, batch[1], batch[2], 4, 10, 2, return_lattices=True)
-    gap = min(l.min_gap for l in lats)
-    if gap > 1e-4:
-        assert hyps == ref_h, "beam tokens differ from the oracle: %r vs %r" % (hyps, ref_h)
-    err = max(abs(a - b) for wa, wb in zip(weights, ref_w) for a, b in zip(wa, wb))
-    assert err < 1e-3, "beam scores differ from the oracle by %g" % err
-    print("[smoke] beam decode OK: %d utterances, tokens identical (min top-k gap %.2e), max score diff %.2e" %
-          (len(hyps), gap, err))
