@@ -73,3 +73,16 @@ def test_struct_layouts_match_the_header(library):
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(library.Dropout), ctypes.sizeof(library.GemmDesc), ctypes.sizeof(library.AttnDesc),
                      ctypes.sizeof(library.BeamDesc)]
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU arm may use it."""
+    import re
+    pkg = os.path.join(ROOT, "pytorch-kaldi-asr_b200")
+    pattern = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith(".py") and pattern.search(open(os.path.join(base, name), encoding="utf-8").read()):
+                offenders.append(os.path.relpath(os.path.join(base, name), ROOT))
+    assert offenders == []
