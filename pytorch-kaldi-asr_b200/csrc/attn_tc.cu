@@ -15,6 +15,7 @@
 // The [B*H, Lq, Lk] probability tensor never exists; rows without an allowed key give 0 output and lse = -inf.
 #include "tc_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace pka {
 
@@ -46,6 +47,10 @@ __device__ __forceinline__ float fast_exp2(float x) {       // MUFU.EX2 (2 ulp);
 constexpr uint32_t kIdescS = make_idesc(AT_BM, AT_BN);                  // S = Q K^T
 constexpr uint32_t kIdescO = make_idesc(AT_BM, AT_D, false, true);      // O = P V  (V is MN-major)
 
+// FAST (PKA_ATTN_FAST=1, default off until measured): chunks of 32 keys whose keys are all allowed (the common case away
+// from the band edge and the padded tail) skip the per-element mask tests, and the tile maximum is taken on the raw
+// scores and scaled once (x -> round(x * c) is monotone for c > 0, so the result is bit-identical).
+template <bool FAST>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const AttnTcP p) {
@@ -178,10 +183,22 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32];
         tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv);
+        if (FAST) {                                // raw maximum; scaled once below
+          if (allow[c] == 0xffffffffu) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(sv[e]) * p.scale_log2);
+            for (int e = 0; e < 32; ++e) t_max = fmaxf(t_max, __uint_as_float(sv[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(sv[e]));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(sv[e]) * p.scale_log2);
+        }
       }
+      if (FAST) t_max *= p.scale_log2;             // scale_log2 > 0: -inf stays -inf
       const float m_new = fmaxf(m_run, t_max);
       const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
       const float alpha = (m_run == -CUDART_INF_F) ? 0.f : fast_exp2(m_run - m_new);
@@ -192,11 +209,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         uint32_t sv[32];
         tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv);
         float pv[32];
+        if (FAST && allow[c] == 0xffffffffu) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float pe = ((allow[c] >> e) & 1u) ? fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use)) : 0.f;
-          l_tile += pe;
-          pv[e] = pe;
+          for (int e = 0; e < 32; ++e) {
+            const float pe = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use));
+            l_tile += pe;
+            pv[e] = pe;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float pe = ((allow[c] >> e) & 1u) ? fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use)) : 0.f;
+            l_tile += pe;
+            pv[e] = pe;
+          }
         }
         if (dc.p > 0.f) {
 #pragma unroll
@@ -271,9 +297,13 @@ extern "C" int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void
   PKA_REQUIRE(out_dtype == PKA_BF16 || out_dtype == PKA_F32, PKA_EUNSUPPORTED, "attn_tc_fwd: out dtype %d", out_dtype);
   PKA_REQUIRE((out_dtype == PKA_BF16 ? d->ldo % 8 : d->ldo % 4) == 0 && aligned16(out), PKA_EALIGN, "attn_tc_fwd: out must be 16-byte aligned rows");
   static bool attr_set = false;
+  static bool fast = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_tc_fwd: cannot opt in to %d bytes of shared memory: %s", AT_SMEM, cudaGetErrorString(e));
+    const char* env = getenv("PKA_ATTN_FAST");
+    fast = env && env[0] == '1' && d->scale > 0.f;
     attr_set = true;
   }
   CUtensorMap mapQ, mapK, mapV;
@@ -291,7 +321,10 @@ extern "C" int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = out; p.lse = lse; p.kmask = key_mask; p.drop = d->drop;
   dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->H, d->B);
-  launch_k(attn_tc_fwd_kernel, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
+  if (fast && d->scale > 0.f)
+    launch_k(attn_tc_fwd_kernel<true>, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
+  else
+    launch_k(attn_tc_fwd_kernel<false>, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
   return check_launch("attn_tc_fwd");
 }
 
