@@ -42,3 +42,12 @@ def golden_state_dict(g, prefix="sd."):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode_at_test_start(request):
+    """Every GPU test starts in the exact fp32 mode, whatever an earlier (failed or interrupted) test left behind."""
+    if "gpu" in request.keywords:
+        from pytorch_kaldi_asr_b200 import ops
+        ops.set_compute_mode("fp32")
+    yield
