@@ -2,6 +2,7 @@
 
     python -m pytorch_kaldi_asr_b200.recipe.initialize_model   (L/initialize_model.py)
     python -m pytorch_kaldi_asr_b200.recipe.train              (L/train.py main; `torchrun --nproc-per-node N` for N GPUs)
+    python -m pytorch_kaldi_asr_b200.recipe.combine            (L/combine.py)
     python -m pytorch_kaldi_asr_b200.recipe.decode             (L/decode.py main)
     python -m pytorch_kaldi_asr_b200.recipe.rescore            (L/rescore.py)
     python -m pytorch_kaldi_asr_b200.recipe.score              (compute-wer + best_wer.sh of P/run.sh:196-203)

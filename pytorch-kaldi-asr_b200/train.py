@@ -417,18 +417,11 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
     return best_accu, best_epoch
 
 
-def combine(opt, epoch, crit, data, num_model=20):
+def combine(opt, epoch, crit, data, num_model=20, device='cuda'):
     """Model averaging of L/train.py:284-322: running mean over the checkpoints of epochs `epoch`, `epoch-1`, ...
     (`num_model` of them, missing files end the walk), evaluated on `data` after every addition; the best average is
-    written to `combined.accuXX.XX.torch`.  -> best accuracy.
-
-    The running mean lives on the GPU in the reference's arithmetic (checkpoint.running_average); the best average is a
-    snapshot (the reference's `best_model` aliases the live module, so it saves the last average whatever its score)."""
-    import math
+    written to `combined.accuXX.XX.torch` under `opt.save_model_dir`.  -> best accuracy."""
     import os
-    import time
-    from . import checkpoint as _ckpt
-    print('[PROCEDURE] combining model with model averaging...')
     files = []
     for i in range(epoch, epoch - num_model, -1):
         name = opt.save_model_dir + '/epoch.{}.torch'.format(i)
@@ -437,14 +430,27 @@ def combine(opt, epoch, crit, data, num_model=20):
         files.append(name)
     if not files:
         raise ValueError('[ERROR] no checkpoint epoch.{}.torch under {}'.format(epoch, opt.save_model_dir))
-    first = _ckpt.load_checkpoint(files[0], device='cuda')
+    return combine_files(files, crit, data, opt.save_model_dir, train_options=opt, device=device)
+
+
+def combine_files(files, crit, data, save_model_dir, train_options=None, device='cuda'):
+    """The averaging loop shared by `combine` and the stand-alone L/combine.py:33-108: running mean of the model files
+    in the given order, evaluation on `data` after every addition, best average saved.  -> best accuracy.
+
+    The running mean lives on the device in the reference's arithmetic (checkpoint.running_average); the best average is
+    a snapshot (the reference's `best_model` aliases the live module, so it saves the last average whatever its score)."""
+    import math
+    import time
+    from . import checkpoint as _ckpt
+    print('[PROCEDURE] combining model with model averaging...')
+    first = _ckpt.load_checkpoint(files[0], device=device)
     model, model_options = first['model'], first['model_options']
     print('[INFO] model loaded')
 
     def states():
-        yield {k: v.to('cuda') for k, v in first['state_dict'].items()}
+        yield {k: v.to(device) for k, v in first['state_dict'].items()}
         for name in files[1:]:
-            yield {k: v.to('cuda') for k, v in _ckpt.read_checkpoint(name)['state_dict'].items()}
+            yield {k: v.to(device) for k, v in _ckpt.read_checkpoint(name)['state_dict'].items()}
 
     best_accu, best_state, best_n = -1.0, None, 0
     for n, avg in _ckpt.running_average(states()):
@@ -458,7 +464,7 @@ def combine(opt, epoch, crit, data, num_model=20):
             best_accu, best_n = test_accu, n
             best_state = {k: v.detach().cpu().clone() for k, v in avg.items()}
     print('[INFO] best combined model with accuracy: {:3.2f} %'.format(100 * best_accu))
-    model_name = opt.save_model_dir + '/combined.accu{:3.2f}.torch'.format(100 * best_accu)
-    _ckpt.save_state(model_name, best_state, model, model_options, first['epoch'], train_options=opt,
-                     extra=dict(averaged_models=best_n, averaged_from=files[:best_n]))
+    model_name = save_model_dir + '/combined.accu{:3.2f}.torch'.format(100 * best_accu)
+    _ckpt.save_state(model_name, best_state, model, model_options, first['epoch'], train_options=train_options,
+                     extra=dict(averaged_models=best_n, averaged_from=list(files[:best_n])))
     return best_accu

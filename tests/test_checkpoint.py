@@ -81,3 +81,35 @@ def test_running_average_equals_the_reference_combine_arithmetic():
     assert seen == 4
     with pytest.raises(ValueError):
         list(ck.running_average([sd, {k: v for k, v in list(sd.items())[:-1]}]))
+
+
+def test_combine_keeps_the_best_running_average(tmp_path, monkeypatch, capsys):
+    """`train.combine` / `combine_files` (L/train.py:284-322, L/combine.py) with the evaluation mocked out: epoch files
+    are walked newest first, missing files end the walk, the best (not the last) average is what gets saved."""
+    from pytorch_kaldi_asr_b200 import train as T
+    _, sd = golden_arrays()
+    raw = ck.read_checkpoint(REF_FILE)
+    model = ck.build_model(raw["model_options"], sd)
+    for epoch in (2, 3, 4, 5):                                   # epoch.1 is missing: the walk from 5 must stop at 2
+        ck.save_state(str(tmp_path / ("epoch.%d.torch" % epoch)), perturbed(sd, epoch), model, raw["model_options"], epoch)
+    scores = iter([(1.0, 0.20), (0.9, 0.50), (0.8, 0.40), (0.7, 0.50)])
+    seen = []
+
+    def fake_epoch(m, data, crit, mode="train", **kw):
+        assert mode == "eval" and not m.training is None
+        seen.append({k: v.detach().clone() for k, v in m.state_dict().items()})
+        return next(scores)
+    monkeypatch.setattr(T, "train_epoch", fake_epoch)
+    opt = argparse.Namespace(save_model_dir=str(tmp_path))
+    best = T.combine(opt, 5, None, data=None, num_model=10, device="cpu")
+    assert best == 0.50 and len(seen) == 4
+    out = ck.read_checkpoint(str(tmp_path / "combined.accu50.00.torch"))
+    assert out["extra"]["averaged_models"] == 2                   # the first 0.50, not the later tie
+    assert [os.path.basename(f) for f in out["extra"]["averaged_from"]] == ["epoch.5.torch", "epoch.4.torch"]
+    want = list(ck.running_average([perturbed(sd, 5), perturbed(sd, 4)]))[-1][1]
+    assert all(torch.equal(out["state_dict"][k], want[k]) for k in want)
+    assert all(torch.equal(seen[1][k], want[k]) for k in want)    # the model evaluated second carried that average
+    assert out["epoch"] == 5 and out["train_options"] == dict(save_model_dir=str(tmp_path))
+    assert "[INFO] averaging 4 models" in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        T.combine(opt, 9, None, data=None, device="cpu")
