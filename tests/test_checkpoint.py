@@ -113,3 +113,47 @@ def test_combine_keeps_the_best_running_average(tmp_path, monkeypatch, capsys):
     assert "[INFO] averaging 4 models" in capsys.readouterr().out
     with pytest.raises(ValueError):
         T.combine(opt, 9, None, data=None, device="cpu")
+
+
+def test_train_driver_checkpoints_and_best_snapshot(tmp_path, monkeypatch, capsys):
+    """`train.train` (L/train.py:217-272) with the epochs mocked out: which epochs are saved, that the best model is the
+    snapshot taken at its epoch (not the live module), that only the writer rank writes, and where a resume starts."""
+    import pytorch_kaldi_asr_b200 as pk
+    from pytorch_kaldi_asr_b200 import train as T
+    _, sd = golden_arrays()
+    raw = ck.read_checkpoint(REF_FILE)
+    model = ck.build_model(raw["model_options"], sd)
+    optimizer = pk.ScheduledOptim(torch.optim.Adam(model.parameters(), betas=(0.9, 0.999), eps=1e-8), 1e-3, 100)
+    probe = "decoder.tgt_word_emb.weight"
+    dev_accuracy = {1: 0.30, 2: 0.35, 3: 0.60, 4: 0.55}
+    calls, state = [], dict(epoch=0)
+
+    def fake_epoch(m, data, crit, mode="train", batch_eval=10, **kw):
+        calls.append((data, mode, batch_eval))
+        if mode == "train":
+            state["epoch"] += 1
+            with torch.no_grad():
+                dict(m.named_parameters())[probe].fill_(float(state["epoch"]))      # "training" marks the weights
+            return 1.0, 0.10
+        return 1.0, (dev_accuracy[state["epoch"]] if data == "dev" else 0.20)
+    monkeypatch.setattr(T, "train_epoch", fake_epoch)
+    opt = argparse.Namespace(epoch=4, save_interval=2, save_model_dir=str(tmp_path), seq_error_prob=0)
+    best_accu, best_epoch = T.train(model, "train", "dev", "test", None, optimizer, opt, raw["model_options"])
+    assert (best_accu, best_epoch) == (0.60, 3)
+    assert calls[:4] == [("train", "train", 10), ("train", "eval", 10), ("dev", "eval", 10), ("test", "eval", 10)]
+    files = sorted(os.listdir(str(tmp_path)))
+    assert files == ["best.epoch3.accu60.00.torch", "epoch.2.torch", "epoch.3.torch", "epoch.4.torch"]
+    best = ck.read_checkpoint(str(tmp_path / files[0]))
+    assert best["epoch"] == 3 and float(best["state_dict"][probe][0, 0]) == 3.0        # the reference would store 4.0
+    assert float(model.state_dict()[probe][0, 0]) == 4.0
+    last = ck.read_checkpoint(str(tmp_path / "epoch.4.torch"))
+    assert last["optimizer"]["schedule"]["n_current_steps"] == 0 and last["train_options"]["save_interval"] == 2
+    assert "best valid accuracy: 60.00 %, on epoch 3" in capsys.readouterr().out
+
+    # a non-writer rank trains and evaluates but writes nothing; a resumed run starts at opt.start_epoch
+    for f in files:
+        os.remove(str(tmp_path / f))
+    state["epoch"], calls[:] = 2, []
+    opt.start_epoch = 3
+    assert T.train(model, "train", "dev", "test", None, optimizer, opt, raw["model_options"], writer=False) == (0.60, 3)
+    assert os.listdir(str(tmp_path)) == [] and sum(1 for c in calls if c[1] == "train") == 2
