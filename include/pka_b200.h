@@ -234,6 +234,14 @@ int pka_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   void* stream);
 int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream);
 
+/* ---- host side of the input feed (no device work) --------------------------------------------------------------------
+ * replaces: pad_to_longest over the features of a batch (U/instances_handler.py:118-139, U/BatchLoader.py:92-103).
+ * Gathers n_utt ragged utterances (numbers idx[]) from a packed frame store frames[total, dim] / offsets[n_total + 1]
+ * into src[n_utt, t_pad, dim] (zero padded) and mask[n_utt, t_pad] (1 = real frame), with up to n_threads threads.
+ * All pointers are HOST memory; src / mask are normally the pinned staging buffers of the H2D copy. */
+int pka_host_pack_batch(const float* frames, const int64_t* offsets, int64_t n_total, const int64_t* idx, int n_utt,
+                        int t_pad, int dim, float* src, uint8_t* mask, int n_threads);
+
 /* ---- data-parallel optimiser step over peer memory (NVLink / NVSwitch) ------------------------------------------
  * replaces, for W ranks: {all-reduce SUM of the gradient arena (the new exchange step of SURVEY.md 8e), pka_adam_step}
  * by ONE kernel per rank: gradient reduce-scatter (multimem.ld_reduce through the switch when multicast addresses

@@ -19,6 +19,9 @@ What is different underneath, because the consumer is a ~1.5 ms GPU step rather 
   the set, which is also what a CUDA-graph replay needs) or `'batch'` (what it does when streaming), independent of
   `pre_load`; `pad_multiple` rounds the frame axis up; `bucket=K` sorts by length inside windows of K batches so that
   'batch' padding wastes little;
+* the feature gather of a pre-loaded batch runs in the native library (`pka_host_pack_batch`; `pack_threads` > 1
+  splits the rows over host threads -- measured: the copy is memory-bound and one thread is fastest on the 8-core
+  build container -- and 0 selects the numpy loop, which the tests hold the native path to bit for bit);
 * `shard=(rank, world)` deals the epoch's batches round-robin to data-parallel ranks (needs `seed` so every rank draws
   the same permutation; in 'drop' mode every rank gets the same number of batches so collectives line up);
 * `read_ahead=n` assembles up to n batches on a background thread when streaming from disk.
@@ -49,7 +52,8 @@ def _numpy_alloc(specs):
 class BatchLoader:
     def __init__(self, trainning_triples, batch_size, pre_load=True, print_info=True, mode='drop', *,
                  pad_to: Optional[str] = None, pad_multiple: int = 1, bucket: int = 0, seed: Optional[int] = None,
-                 shard: Tuple[int, int] = (0, 1), read_ahead: int = 0, reader: Optional[Callable] = None):
+                 shard: Tuple[int, int] = (0, 1), read_ahead: int = 0, reader: Optional[Callable] = None,
+                 pack_threads: int = 1):
         if mode not in ('all', 'drop'):
             raise ValueError('[ERROR] mode of BatchLoader can only be [all] or [drop]')
         if batch_size < 1:
@@ -70,6 +74,7 @@ class BatchLoader:
         self.bucket = int(bucket)
         self.shard = (rank, world)
         self.read_ahead = int(read_ahead)
+        self.pack_threads = int(pack_threads)
         self._rng = random if seed is None else random.Random(seed)
         self._read = reader or kaldi_ark.read_mat
 
@@ -199,13 +204,18 @@ class BatchLoader:
         b = len(idx)
         src, src_mask, tgt, tgt_mask = alloc([((b, t_pad, dim), _DTYPES[0]), ((b, t_pad), _DTYPES[1]),
                                               ((b, l_pad), _DTYPES[2]), ((b, l_pad), _DTYPES[3])])
+        native = (mats is None and self.pack_threads > 0 and b > 0 and src.flags['C_CONTIGUOUS']
+                  and src_mask.flags['C_CONTIGUOUS'])
+        if native:
+            self._native_pack(idx, t_pad, src, src_mask)
         for row, i in enumerate(idx):
-            m = mats[row] if mats is not None else self._utt(i)
-            t = m.shape[0]
-            src[row, :t] = m
-            src[row, t:] = constants.PAD
-            src_mask[row, :t] = 1
-            src_mask[row, t:] = 0
+            if not native:
+                m = mats[row] if mats is not None else self._utt(i)
+                t = m.shape[0]
+                src[row, :t] = m
+                src[row, t:] = constants.PAD
+                src_mask[row, :t] = 1
+                src_mask[row, t:] = 0
             lab = self._tgt[i]
             n = lab.shape[0]
             tgt[row, :n] = lab
@@ -213,6 +223,15 @@ class BatchLoader:
             tgt_mask[row, :n] = 1
             tgt_mask[row, n:] = 0
         return tuple(self.keys[i] for i in idx), src, src_mask, tgt, tgt_mask
+
+    def _native_pack(self, idx, t_pad, src, src_mask):
+        import ctypes as C
+        from .. import _lib as L
+        order = np.ascontiguousarray(idx, dtype=np.int64)
+        L.check(L.lib().pka_host_pack_batch(C.c_void_p(self._frames.ctypes.data), C.c_void_p(self._offsets.ctypes.data),
+                                            C.c_int64(len(self.keys)), C.c_void_p(order.ctypes.data), len(order),
+                                            int(t_pad), int(self.feat_dim), C.c_void_p(src.ctypes.data),
+                                            C.c_void_p(src_mask.ctypes.data), self.pack_threads), "host_pack_batch")
 
     def next_into(self, alloc) -> tuple:
         """next(), with the four arrays written into buffers from `alloc([(shape, dtype) x 4]) -> [ndarray x 4]`."""
