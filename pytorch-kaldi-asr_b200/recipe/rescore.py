@@ -1,19 +1,22 @@
-"""LM rescoring entry point -- flags of L/rescore.py:12-21."""
+"""LM rescoring entry point: the command line of L/rescore.py:12-21 in front of `results.rescore`.
+
+`-inv_weight_list 5,10,15` -- each weight DIVIDES the language-model score; one `rescore_<w>` file per weight is written
+to `-save_dir`, holding the best hypothesis of every utterance of `-decode_file` under `model + lm / w`."""
 import argparse
+
+FLAGS = ('decode_file', 'lm_score', 'save_dir', 'inv_weight_list')
 
 
 def main(argv=None):
     from .. import results
-    parser = argparse.ArgumentParser()
-    parser.add_argument('-decode_file', required=True)
-    parser.add_argument('-lm_score', required=True)
-    parser.add_argument('-save_dir', required=True)
-    parser.add_argument('-inv_weight_list', required=True)        # '5,10,15': the weight divides the LM score
+    parser = argparse.ArgumentParser(description=__doc__)
+    for name in FLAGS:
+        parser.add_argument('-' + name, required=True)
     opt = parser.parse_args(argv)
     print('[PROCEDURE] start rescoring...')
-    files = results.rescore(opt.decode_file, opt.lm_score, opt.save_dir, opt.inv_weight_list)
-    print('[INFO] rescoring finished')
-    return files
+    written = results.rescore(opt.decode_file, opt.lm_score, opt.save_dir, opt.inv_weight_list)
+    print('[INFO] rescoring finished: {} files'.format(len(written)))
+    return written
 
 
 if __name__ == '__main__':
