@@ -98,7 +98,19 @@ def optimizer_state(optimizer, model=None) -> dict:
     inner = getattr(optimizer, "optimizer", optimizer)
     state = dict(adam=_cpu(inner.state_dict()))
     if inner is not optimizer:
-        state["schedule"] = dict(n_current_steps=int(optimizer.n_current_steps), start_lr=float(optimizer.start_lr),
+        n_steps = int(optimizer.n_current_steps)
+        fused = state["adam"].get("fused")
+        if fused is not None:
+            # A CUDA-graph step advances the schedule on the device only (train.GraphedTrainStep): the device counter
+            # is the truth, the host-side mirror and the param-group lr are brought in line before they are written
+            n_steps = max(n_steps, int(fused["n_current_steps"]))
+            if n_steps != int(optimizer.n_current_steps):
+                optimizer.n_current_steps = n_steps
+                lr = (optimizer.start_lr * optimizer.soft_coefficient) / (n_steps + optimizer.soft_coefficient)
+                for group in inner.param_groups:
+                    group["lr"] = lr
+                state["adam"] = _cpu(inner.state_dict())
+        state["schedule"] = dict(n_current_steps=n_steps, start_lr=float(optimizer.start_lr),
                                  soft_coefficient=float(optimizer.soft_coefficient))
     if model is not None and hasattr(model, "dropout_state"):
         rng = model.dropout_state
@@ -162,13 +174,29 @@ def save_checkpoint(path, model, model_options, epoch, train_options=None, optim
     return save_state(path, model.state_dict(), model, model_options, epoch, train_options, optimizer, extra)
 
 
-def read_checkpoint(path) -> dict:
+def _pickle_allowed(allow_pickle) -> bool:
+    if allow_pickle is not None:
+        return bool(allow_pickle)
+    return os.environ.get("PKA_ALLOW_PICKLE", "1") != "0"
+
+
+def read_checkpoint(path, allow_pickle=None) -> dict:
     """File -> {'state_dict', 'model_options', 'epoch', 'train_options', 'optimizer', 'extra'} without building a model.
-    Reference-format files (pickled module) need `pytorch_kaldi_asr_b200.dropin` so that their class paths resolve."""
+    Files of this package are plain data and load with `weights_only=True`.  Reference-format files (a pickled
+    nn.Module + argparse.Namespace, L/train.py:252-262) can only be read by unpickling, which executes code from the
+    file: that path is taken only when the safe loader rejects the file *as a pickle of non-plain objects*, and only if
+    allowed (`allow_pickle=True`, or unset with PKA_ALLOW_PICKLE != "0"; trusted local files only, like the reference).
+    A missing, truncated or otherwise unreadable file raises the original error instead of being retried unsafely."""
+    import pickle
     try:
         raw = torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:
-        # pickled nn.Module / argparse.Namespace: the reference's format (trusted local files only, like the reference)
+    except pickle.UnpicklingError as exc:
+        # torch raises UnpicklingError("Weights only load failed ... Unsupported global ...") for pickled classes
+        if "Unsupported" not in str(exc) and "weights_only" not in str(exc).lower() and "Weights only" not in str(exc):
+            raise
+        if not _pickle_allowed(allow_pickle):
+            raise RuntimeError("[ERROR] %s holds pickled objects (reference checkpoint format); pass allow_pickle=True "
+                               "or set PKA_ALLOW_PICKLE=1 to unpickle it (only for files you trust)" % path) from exc
         from . import dropin                                     # noqa: F401  (registers transformer.*, TDNN, utils.*)
         raw = torch.load(path, map_location="cpu", weights_only=False)
     if not isinstance(raw, dict):
@@ -182,9 +210,9 @@ def read_checkpoint(path) -> dict:
     raise ValueError("[ERROR] %s: unknown checkpoint layout (keys: %s)" % (path, sorted(raw)))
 
 
-def load_checkpoint(path, device=None) -> dict:
+def load_checkpoint(path, device=None, allow_pickle=None) -> dict:
     """-> the checkpoint dictionary plus 'model': a Transformer of this package with the weights loaded."""
-    ckpt = dict(read_checkpoint(path))
+    ckpt = dict(read_checkpoint(path, allow_pickle))
     ckpt["model"] = build_model(ckpt["model_options"], ckpt["state_dict"], device)
     return ckpt
 

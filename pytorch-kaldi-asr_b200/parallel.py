@@ -72,6 +72,7 @@ class GradAllReduce:
         self.comm_stream = torch.cuda.Stream() if (self.is_cuda and self.overlap) else None
         self.launched = [False] * len(self.bounds)
         self.handles = []
+        self.enabled = True
         if self.overlap:
             for i, p in enumerate(params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
@@ -98,6 +99,8 @@ class GradAllReduce:
 
     def _make_hook(self, i):
         def hook(_param):
+            if not self.enabled:
+                return
             b = self.owner[i]
             self.pending[b] -= 1
             if self.pending[b] == 0:
@@ -117,8 +120,24 @@ class GradAllReduce:
         else:
             self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def paused(self):
+        """Context manager: backward passes inside it exchange nothing (single-process reference runs on one rank, e.g.
+        the DP-vs-single-process gradient check of bench.py)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.enabled = False
+            try:
+                yield self
+            finally:
+                self.enabled = True
+        return cm()
+
     def finish(self):
         """Send whatever has not gone out yet (no-overlap mode: everything), then join communication and compute."""
+        if not self.enabled:
+            return
         if self.symm_op is not None:
             self.symm_op(self.opt.flat_grad, "sum", self.group_name)
             return

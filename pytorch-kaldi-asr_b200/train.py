@@ -277,39 +277,86 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
 
 class GraphedTrainStep:
     """Whole training step (zero_grad, forward, loss, backward, [gradient all-reduce], Adam, LR tick, dropout tick)
-    captured once into a CUDA graph and replayed per batch.  Requires fixed batch shapes -- which is what the
-    reference's pre-loading BatchLoader produces (it pads the whole data set to one length, U/BatchLoader.py:33-36).
+    captured into CUDA graphs -- one per batch shape -- and replayed per batch.
 
-    Inputs are copied into static device buffers; `step` returns a device tensor [loss_sum, n_correct, n_words]."""
+    The reference's pre-loading BatchLoader pads the whole data set to one length (U/BatchLoader.py:33-36): one shape,
+    one graph.  With per-batch padding to a few bucket lengths (`utils.BatchLoader(pad_to="bucket", bucket=...)`) every
+    bucket shape gets its own graph, captured the first time the shape is seen (or up front with `capture`); the graphs
+    share one memory pool (they never run concurrently and no tensor created inside one outlives its replay).
 
-    def __init__(self, model, optimizer, example_batch, smoothing=False, grad_sync=None, warmup=3):
+    Inputs are copied into the shape's static device buffers; `step` returns a device tensor
+    [loss_sum, n_correct, n_words]."""
+
+    def __init__(self, model, optimizer, example_batch=None, smoothing=False, grad_sync=None, warmup=3):
         self.model, self.optimizer, self.smoothing, self.grad_sync = model, optimizer, smoothing, grad_sync
-        device = next(model.parameters()).device
-        src, smask, tgt, tmask = _to_device(example_batch, device, non_blocking=False)
-        self.src, self.smask, self.tgt, self.tmask = src.clone(), smask.clone(), tgt.clone(), tmask.clone()
-        self.out = torch.zeros(3, device=device, dtype=torch.float32)
+        self.device = next(model.parameters()).device
+        self.out = torch.zeros(3, device=self.device, dtype=torch.float32)
+        self.warmup = warmup
+        self.shapes = {}                                  # (B, T, F, L+1) -> dict(src, smask, tgt, tmask, graph)
+        self.pool = None
+        self.cur = None
+        if example_batch is not None:
+            self.capture(example_batch)
+
+    # -- the most recently used shape, under the names the single-shape version exposed
+    @property
+    def graph(self):
+        return self.cur["graph"]
+
+    @property
+    def src(self):
+        return self.cur["src"]
+
+    @property
+    def tgt(self):
+        return self.cur["tgt"]
+
+    @staticmethod
+    def _key(src, tgt):
+        return tuple(src.shape) + (int(tgt.shape[1]),)
+
+    def capture(self, batch):
+        """Make sure a graph exists for this batch's shape (batch tuple of numpy arrays or device tensors)."""
+        if len(batch) == 5:
+            batch = batch[1:]
+        key = self._key(batch[0], batch[2])
+        ent = self.shapes.get(key)
+        if ent is None:
+            ent = self.shapes[key] = self._capture(batch)
+        self.cur = ent
+        return ent
+
+    def _capture(self, batch):
+        model, device = self.model, self.device
+        src, smask, tgt, tmask = _to_device((None,) + tuple(batch), device, non_blocking=False)
+        ent = dict(src=src.clone(), smask=smask.clone(), tgt=tgt.clone(), tmask=tmask.clone(), graph=None)
+        was_training = model.training
         model.train()
         snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):                       # warm allocator pools & lazy state outside the capture
-                self._body()
+            for _ in range(self.warmup if not self.shapes else 1):     # warm allocator pools & lazy state outside the capture
+                self._body(ent)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        ent["graph"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ent["graph"], pool=self.pool):
+            self._body(ent)
         self._restore(snap)                               # warm-up steps must not count as training
+        model.train(was_training)
+        return ent
 
     def _snapshot(self):
         inner = getattr(self.optimizer, "optimizer", self.optimizer)
         if not hasattr(inner, "flat_param"):
             raise RuntimeError("GraphedTrainStep needs a FusedAdam (flat parameter arena) inside the optimizer")
         rng = self.model.dropout_state
-        dev = self.src.device
+        dev = self.device
         return dict(tensors=[(t, t.clone()) for t in (inner.flat_param, inner.exp_avg, inner.exp_avg_sq, inner.dev_state,
-                                                      inner.dev_lr, rng.step_tensor(dev))],
+                                                      inner.dev_lr, rng.step_tensor(dev), self.out)],
                     n=getattr(self.optimizer, "n_current_steps", None), lr=[g["lr"] for g in inner.param_groups])
 
     def _restore(self, snap):
@@ -324,10 +371,11 @@ class GraphedTrainStep:
             g["lr"] = lr
         torch.cuda.synchronize()
 
-    def _body(self):
-        goal = self.tgt[:, 1:]
+    def _body(self, ent):
+        tgt = ent["tgt"]
+        goal = tgt[:, 1:]
         self.optimizer.zero_grad()
-        pred = self.model(self.src, self.smask, self.tgt[:, :-1], self.tmask[:, :-1])
+        pred = self.model(ent["src"], ent["smask"], tgt[:, :-1], ent["tmask"][:, :-1])
         loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), self.smoothing)
         loss.backward()
         if self.grad_sync is not None:
@@ -338,19 +386,39 @@ class GraphedTrainStep:
         self.out[1:].copy_(stats)
 
     def load(self, src, smask, tgt, tmask):
-        self.src.copy_(src, non_blocking=True)
-        self.smask.copy_(smask, non_blocking=True)
-        self.tgt.copy_(tgt, non_blocking=True)
-        self.tmask.copy_(tmask, non_blocking=True)
+        ent = self.shapes.get(self._key(src, tgt))
+        if ent is None:
+            ent = self.capture((src, smask, tgt, tmask))
+        self.cur = ent
+        ent["src"].copy_(src, non_blocking=True)
+        ent["smask"].copy_(smask, non_blocking=True)
+        ent["tgt"].copy_(tgt, non_blocking=True)
+        ent["tmask"].copy_(tmask, non_blocking=True)
+        return ent
 
     def step(self, src, smask, tgt, tmask):
-        if tuple(src.shape) != tuple(self.src.shape) or tuple(tgt.shape) != tuple(self.tgt.shape):
-            raise RuntimeError("GraphedTrainStep: batch shape %s/%s differs from the captured %s/%s; pad the data set "
-                               "to one length (synthetic.batches(pad_to='set'))" %
-                               (tuple(src.shape), tuple(tgt.shape), tuple(self.src.shape), tuple(self.tgt.shape)))
-        self.load(src, smask, tgt, tmask)
-        self.graph.replay()
+        ent = self.load(src, smask, tgt, tmask)
+        ent["graph"].replay()
+        self._host_tick()
         return self.out
+
+    def _host_tick(self):
+        """Keep the host-side mirror of the LR schedule in step with the device counters the graph advances (a
+        checkpoint written after graphed training must carry the right schedule step; the arithmetic is
+        ScheduledOptim.update_learning_rate's, no kernel)."""
+        opt = self.optimizer
+        if hasattr(opt, "n_current_steps") and hasattr(opt, "soft_coefficient"):
+            opt.n_current_steps += 1
+            new_lr = (opt.start_lr * opt.soft_coefficient) / (opt.n_current_steps + opt.soft_coefficient)
+            for group in opt.optimizer.param_groups:
+                group["lr"] = new_lr
+
+    def release(self):
+        """Drop the captured graphs (before tearing down a process group whose collectives they contain)."""
+        for ent in self.shapes.values():
+            ent["graph"] = None
+        self.shapes.clear()
+        self.cur = None
 
 
 # ------------------------------------------------------------------------------------------------ epoch driver

@@ -10,10 +10,16 @@ import numpy as np
 from . import constants
 
 
-def pad_to_longest(instances):
-    """list of 1-D (labels) or 2-D (frames x dim) arrays -> (stacked array padded with PAD, uint8 mask [n, max_len])."""
+def pad_to_longest(instances, length=None):
+    """list of 1-D (labels) or 2-D (frames x dim) arrays -> (stacked array padded with PAD, uint8 mask [n, max_len]).
+    `length` (extension; the reference pads to the longest instance, U/instances_handler.py:118-139) pads further, to a
+    bucket length >= the longest instance."""
     lengths = [len(x) for x in instances]
     longest = max(lengths)
+    if length is not None:
+        if length < longest:
+            raise ValueError("pad_to_longest: length %d is shorter than the longest instance (%d)" % (length, longest))
+        longest = int(length)
     first = np.asarray(instances[0])
     if first.ndim not in (1, 2):
         raise ValueError("undefined padding shape: instances must be 1-D or 2-D arrays")

@@ -35,9 +35,26 @@ def batches(n_batches: int, batch_size: int, seed: int = 1234, pad_to: str = "ba
 
     pad_to="batch": pad each batch to its own longest utterance (pad_to_longest).
     pad_to="set":   pad every batch to the longest utterance of the whole set, like the reference's pre-loading
-                    BatchLoader (U/BatchLoader.py:33-36) -- all batches then share one shape (one CUDA graph)."""
+                    BatchLoader (U/BatchLoader.py:33-36) -- all batches then share one shape (one CUDA graph).
+    pad_to="bucket": utterances sorted by length into batches (batch order shuffled), each batch padded to
+                    bucket_length(longest, set length); labels to a multiple of 8 tokens (a few shapes, one graph each)."""
     rng = np.random.RandomState(seed)
     feats, labels = utterances(n_batches * batch_size, rng, **kw)
+    if pad_to == "bucket":
+        t_set = max(f.shape[0] for f in feats)
+        order = np.argsort([f.shape[0] for f in feats], kind="stable")
+        out = []
+        # the batch order is the same for every seed: data-parallel ranks (one seed each) then step through their
+        # length quantiles in the same order and see similar shapes in the same step (no straggler rank)
+        for b in np.random.RandomState(4321).permutation(n_batches):
+            idx = order[b * batch_size:(b + 1) * batch_size]
+            fs, ls = [feats[i] for i in idx], [labels[i] for i in idx]
+            t_pad = bucket_length(max(f.shape[0] for f in fs), t_set)
+            l_pad = (max(len(l) for l in ls) - 1 + 7) // 8 * 8 + 1
+            src, smask = pad_to_longest(fs, t_pad)
+            tgt, tmask = pad_to_longest(ls, l_pad)
+            out.append((["utt%06d" % i for i in idx], src, smask, tgt, tmask))
+        return out
     if pad_to == "set":
         src_all, smask_all = pad_to_longest(feats)
         tgt_all, tmask_all = pad_to_longest(labels)
@@ -52,6 +69,14 @@ def batches(n_batches: int, batch_size: int, seed: int = 1234, pad_to: str = "ba
             tgt, tmask = pad_to_longest(labels[sl])
             out.append((keys, src, smask, tgt, tmask))
     return out
+
+
+def bucket_length(longest: int, set_length: int, context: int = 16, quantum: int = 64) -> int:
+    """Padded length of a batch whose longest utterance has `longest` frames: at least `context` pad frames behind
+    every utterance (the TDNN stack's right receptive field, SURVEY 8e: the encoder output of real frames is then
+    independent of any further padding), rounded up to `quantum`, never beyond the whole-set length the reference
+    pads to (a batch that long sees exactly the reference's padding)."""
+    return int(min((longest + context + quantum - 1) // quantum * quantum, set_length))
 
 
 def real_frames(batch) -> int:
