@@ -113,8 +113,14 @@ typedef struct {
   int32_t shift[PKA_MAX_CTX];
   int32_t relu, c_dtype, splits, reserved;
   pka_dropout drop;
+  const void* addend;      /* mode 0, optional: bf16 [Bt*T, ldadd], C = epi(...) + addend -- the residual branch of a      */
+  int32_t ldadd, reserved2;/* gradient (dX = dZ.W + dResidual) folded into the data-gradient GEMM's epilogue             */
 } pka_tc_desc;
 int pka_gemm_tc(const pka_tc_desc* d, void* stream);
+/* n_desc independent mode-2 (weight-gradient) problems in ONE launch: the decoder-shaped gradients of a backward pass
+ * (a few output tiles each, ~6 us when launched alone) are not on the critical path, so they are collected and run as
+ * one grid at the end of backward.  Same partial layout as pka_gemm_tc mode 2 (C = fp32 [splits, M, ldc]). */
+int pka_gemm_tc_wgrad_group(const pka_tc_desc* descs_host, int n_desc, void* stream);
 /* out[e] (+)= sum_{s<splits} ws[s*per + e] */
 int pka_tc_reduce(const float* ws, float* out, int64_t per, int splits, int accumulate, void* stream);
 /* fp32 W[N, nseg*K] -> Wf bf16 (same layout, forward operand) and/or Wd bf16 [K, nseg*N], Wd[i, s*N+o] = W[o, s*K+i] */
@@ -129,6 +135,41 @@ int pka_head_grad_relayout(const float* dWcat, float* g0, float* g1, float* g2, 
 /* pka_tc_reduce + pka_head_grad_relayout in one launch: g_p[h,d,j] = sum_{s<splits} ws[s][(p*H+h)*dk+j][d] (fixed order) */
 int pka_tc_reduce_heads(const float* ws, float* g0, float* g1, float* g2, int splits, int P, int H, int D, int dk,
                         void* stream);
+
+/* ---- batched helper launches of the training step (csrc/batched.cu) ---------------------------------------------
+ * The reference's optimiser sees finished gradients because ATen finishes every reduction inside its op
+ * (torch.autograd of Linear / LayerNormalization / bmm: L/train.py:197-199 calls backward() then step()).  Here the
+ * backward kernels leave fixed-order split partials behind (weight-gradient splits, bias / LayerNorm column sums,
+ * packed per-head gradients) and ONE launch per backward pass sums them all into the gradient arena:
+ *   PLAIN: dst[e] (+)= sum_{s<splits} src[s*split_stride + e],  e < n
+ *   HEADS: dst[(h*D + d)*dk + j] = sum_s src[s*split_stride + (h*dk + j)*D + d]   (one block [(h,j), d] of a packed
+ *          head-projection gradient -> the reference's per-head layout [H, D, dk], T/SubLayers.py:29-31); n = H*D*dk.
+ * Summation order is a fixed function of (splits), independent of the launch: bit-reproducible. */
+enum { PKA_REDUCE_PLAIN = 0, PKA_REDUCE_HEADS = 1 };
+#define PKA_MAX_REDUCE_JOBS 128
+typedef struct {
+  const float* src; float* dst;
+  int64_t n, split_stride;
+  int32_t splits, kind, accumulate, D, dk, reserved;
+} pka_reduce_job;
+int pka_reduce_jobs(const pka_reduce_job* jobs_host, int n_jobs, void* stream);
+/* ONE launch refreshes the bf16 GEMM operand copies of all fp32 master weights (they change only in the optimiser
+ * step; round 1 re-made them in every forward, 29 launches) and, optionally, advances the dropout step counter:
+ *   PLAIN: src fp32 [N, nseg*K] -> wf bf16 [N, ldf] (same element order) and/or wd bf16 [K, ldd], wd[i, s*N+o] = src[o, s*K+i]
+ *   HEADS: src fp32 [H=N, D=K, dk=nseg] -> rows n0 + h*dk + j of wf[.., ldf] (wf[n, d]) and columns n0 + h*dk + j of
+ *          wd [D, ldd] (wd[d, n]): one block of a packed q|k|v operand (or of the k|v operand of several layers). */
+enum { PKA_RELAYOUT_PLAIN = 0, PKA_RELAYOUT_HEADS = 1 };
+#define PKA_MAX_RELAYOUT_JOBS 128
+typedef struct {
+  const float* src; void* wf; void* wd;
+  int32_t N, K, nseg, kind, ldf, ldd, n0, reserved;
+} pka_relayout_job;
+int pka_relayout_jobs(const pka_relayout_job* jobs_host, int n_jobs, uint64_t* step_counter, void* stream);
+/* teacher-forcing split of L/train.py:163-165 in one launch: tgt i64[B,L1], mask u8[B,L1] ->
+ * tgt_in = tgt[:, :-1], goal = tgt[:, 1:], mask_in = mask[:, :-1]  (contiguous [B, L1-1]) */
+int pka_split_targets(const int64_t* tgt, const uint8_t* mask, int64_t* tgt_in, int64_t* goal, uint8_t* mask_in, int B,
+                      int L1, void* stream);
+
 /* dZ = gate ? ((Y > 0) ? dY*scale : 0) : dY, bf16, written row-major [Bt*T, N] (dZ) and transposed [N, Bt, Tp] (dZt) */
 int pka_relu_bwd_dual(const void* dY, int dy_dtype, const void* Y, void* dZ, void* dZt, int Bt, int T, int Tp, int N,
                       float scale, int gate, void* stream);
@@ -176,7 +217,9 @@ int pka_attn_tc_bwd(const pka_attn_desc* d, const void* q, const void* k, const 
 int pka_add_layernorm_fwd(const void* x, const void* residual, const float* a, const float* b, void* y, float* mean,
                           float* rinv, int dtype, int rows, int D, float eps, const pka_dropout* drop, void* stream);
 /* dres always written; dx written only when drop->p > 0 (otherwise dx == dres and may be NULL).
- * dab_ws: float[2*D*pka_ln_bwd_blocks(rows)] scratch; da/db are overwritten. */
+ * dab_ws: float[3*D*pka_ln_bwd_blocks(rows)] scratch, layout [block][da | db | column sums of the dx written][D]
+ * (the third plane is the bias gradient of a linear layer that produced x); da/db are overwritten.
+ * da == db == NULL: the caller sums the pka_ln_bwd_blocks(rows) partial rows itself (pka_reduce_jobs). */
 int pka_ln_bwd_blocks(int rows);
 int pka_add_layernorm_bwd(const void* dy, const void* x, const void* residual, const float* a, const float* mean,
                           const float* rinv, void* dx, void* dres, float* da, float* db, float* dab_ws, int dtype,
@@ -209,8 +252,13 @@ int pka_dropout_bwd(const void* dy, void* dx, int dtype, int64_t n, const pka_dr
 /* dz = (y > 0) ? dy * scale : 0  -- backward of ReLU followed by dropout, using only the layer output y
  * (y > 0  <=>  pre-activation > 0 and kept).  scale = 1/(1-p). */
 int pka_relu_drop_bwd(const void* dy, const void* y, void* dz, int dtype, int64_t n, float scale, void* stream);
-/* out[n] (+)= sum_r x[r*ld + n]; part_ws float[pka_colsum_chunks(rows)*N]; deterministic two-stage reduction */
+/* out[n] (+)= sum_r x[r*ld + n]; part_ws float[pka_colsum_chunks(rows)*N]; deterministic two-stage reduction.
+ * out == NULL (here and in pka_gate_colsum): only the partial rows are written, the caller sums the
+ * pka_colsum_chunks(rows) rows of part_ws itself (pka_reduce_jobs). */
 int pka_colsum_chunks(int64_t rows);
+/* partial rows actually written for these arguments (<= pka_colsum_chunks(rows)) */
+int pka_colsum_parts(const void* x, const float* part_ws, int dtype, int64_t rows, int N, int ld);
+int pka_gate_colsum_parts(int dy_dtype, int64_t rows, int N);
 int pka_colsum(const void* x, float* out, float* part_ws, int dtype, int64_t rows, int N, int ld, int accumulate,
                void* stream);
 /* one pass: dZ (bf16 [rows,N]) = gate ? ((Y > 0) ? dY*scale : 0) : dY, and out[n] = sum_r dZ[r,n] (bias gradient of a

@@ -41,7 +41,7 @@ class TcDesc(C.Structure):
                 ("a_seg_col", C.c_int32), ("b_seg_col", C.c_int32),
                 ("shift", C.c_int32 * MAX_CTX),
                 ("relu", C.c_int32), ("c_dtype", C.c_int32), ("splits", C.c_int32), ("reserved", C.c_int32),
-                ("drop", Dropout)]
+                ("drop", Dropout), ("addend", C.c_void_p), ("ldadd", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class AttnDesc(C.Structure):
@@ -49,6 +49,22 @@ class AttnDesc(C.Structure):
                 ("dv", C.c_int32), ("ldq", C.c_int32), ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32),
                 ("use_band", C.c_int32), ("band_start", C.c_int32), ("band_end", C.c_int32), ("scale", C.c_float),
                 ("drop", Dropout)]
+
+
+class ReduceJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int64), ("split_stride", C.c_int64),
+                ("splits", C.c_int32), ("kind", C.c_int32), ("accumulate", C.c_int32), ("D", C.c_int32),
+                ("dk", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RelayoutJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p),
+                ("N", C.c_int32), ("K", C.c_int32), ("nseg", C.c_int32), ("kind", C.c_int32),
+                ("ldf", C.c_int32), ("ldd", C.c_int32), ("n0", C.c_int32), ("reserved", C.c_int32)]
+
+
+REDUCE_PLAIN, REDUCE_HEADS = 0, 1
+RELAYOUT_PLAIN, RELAYOUT_HEADS = 0, 1
 
 
 class BeamDesc(C.Structure):

@@ -39,6 +39,7 @@ struct TcParams {
   int utt_per_split, tb_per_utt;
   int dbg;                     // diagnostics (env PKA_TC_DBG): 1 = skip the MMAs, 2 = skip the TMA loads
   pka_dropout drop;
+  const __nv_bfloat16* addend; int ld_add;       // mode 0, optional: C = epi(acc) + addend[m, n]
 };
 
 // instruction descriptors: D=F32, A=B=BF16, N=128, M=128; both K-major (modes 0/1) or both MN-major (mode 2)
@@ -46,8 +47,10 @@ constexpr uint32_t kIdesc = make_idesc(TC_BM, TC_BN);
 constexpr uint32_t kIdescMN = make_idesc(TC_BM, TC_BN, true, true);
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+// bx / by / bz: the CTA's coordinates inside ITS problem's grid (== blockIdx for the single-problem kernel; decoded from
+// a flat CTA index by the grouped kernel below)
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p,
+                                             const int bx, const int by, const int bz) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -60,16 +63,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // ---- tile coordinates
   int b0 = 0, t0 = 0, n0 = 0, seg_fixed = 0, num_k_iters, b_lo = 0;
   if (p.mode == 0) {
-    b0 = blockIdx.x / p.tiles_per_utt;
-    t0 = (blockIdx.x % p.tiles_per_utt) * TC_BM;
-    n0 = blockIdx.y * TC_BN;
+    b0 = bx / p.tiles_per_utt;
+    t0 = (bx % p.tiles_per_utt) * TC_BM;
+    n0 = by * TC_BN;
     num_k_iters = p.nseg * p.kb_per_seg;
   } else {
-    t0 = blockIdx.x * TC_BM;                       // output-channel (row) tile of dW
+    t0 = bx * TC_BM;                               // output-channel (row) tile of dW
     const int i_tiles = (p.N + TC_BN - 1) / TC_BN;
-    seg_fixed = blockIdx.y / i_tiles;
-    n0 = (blockIdx.y % i_tiles) * TC_BN;
-    b_lo = blockIdx.z * p.utt_per_split;
+    seg_fixed = by / i_tiles;
+    n0 = (by % i_tiles) * TC_BN;
+    b_lo = bz * p.utt_per_split;
     int b_hi = min(p.Bt, b_lo + p.utt_per_split);
     num_k_iters = max(0, b_hi - b_lo) * p.tb_per_utt;
   }
@@ -191,6 +194,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
           }
         }
+        if (p.addend && valid) {
+          const __nv_bfloat16* ar = p.addend + m * p.ld_add + nb;
+#pragma unroll 4
+          for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __bfloat162float(ar[j]);
+        }
         if (valid) {
           if (p.c_dtype == PKA_BF16) {
             __nv_bfloat16* dst = (__nv_bfloat16*)p.C + m * p.ldc + nb;
@@ -227,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       } else {                                     // modes 1/2: fp32 partial of dW rows (output channels)
         const int o = t0 + row;
         if (o < p.M) {
-          float* dst = (float*)p.C + ((long long)blockIdx.z * p.M + o) * p.ldc + (long long)seg_fixed * p.N + nb;
+          float* dst = (float*)p.C + ((long long)bz * p.M + o) * p.ldc + (long long)seg_fixed * p.N + nb;
           if (full && (p.ldc & 3) == 0 && (p.N & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -246,6 +254,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  gemm_tc_body(mapA, mapB, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Grouped launch: up to TC_GROUP independent problems (the decoder-shaped weight gradients of one backward pass: 128- or
+// 384-row outputs, reduction over the B*L tokens or B*T frames, ~32 CTAs and ~6 us each when launched alone) share ONE
+// grid; a CTA finds its problem by a binary search over the prefix sums of the problems' grid sizes.  Tensor maps and
+// parameters of all problems travel as __grid_constant__ kernel parameters (CUDA 12.1+: 32 KB parameter space).
+constexpr int TC_GROUP = 40;
+struct TcGroup {
+  CUtensorMap mapA[TC_GROUP];
+  CUtensorMap mapB[TC_GROUP];
+  TcParams p[TC_GROUP];
+  int cta_start[TC_GROUP + 1];
+  int gx[TC_GROUP], gy[TC_GROUP];
+  int n;
+};
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_tc_group_kernel(const __grid_constant__ TcGroup g) {
+  int lo = 0, hi = g.n;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (g.cta_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid; }
+  const int r = (int)blockIdx.x - g.cta_start[lo];
+  const int gx = g.gx[lo], gxy = gx * g.gy[lo];
+  gemm_tc_body(g.mapA[lo], g.mapB[lo], g.p[lo], r % gx, (r % gxy) / gx, r / gxy);
 }
 
 // fixed-order sum of the split partials: out[m, n] (+)= sum_s ws[s][m][n]
@@ -386,6 +421,7 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
   PKA_REQUIRE(d && d->A && d->B && d->C, PKA_EINVAL, "gemm_tc: null operand");
   PKA_REQUIRE(d->Bt > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->nseg >= 1 && d->nseg <= PKA_MAX_CTX, PKA_EINVAL,
               "gemm_tc: bad sizes Bt=%d T=%d N=%d K=%d nseg=%d", d->Bt, d->T, d->N, d->K, d->nseg);
+  PKA_REQUIRE(!d->addend || (d->mode == 0 && d->ldadd >= d->N && !d->Ct), PKA_EINVAL, "gemm_tc: addend needs mode 0, ldadd >= N, no transposed copy");
   if (d->mode == 0) {                              // A-stationary / B-multicast kernel whenever the problem fits it
     PKA_REQUIRE(d->nseg == 1 || d->K % TC_BK == 0, PKA_EUNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d when nseg>1", d->K, TC_BK);
     PKA_REQUIRE(d->drop.p == 0.f || d->N % 4 == 0, PKA_EUNSUPPORTED, "gemm_tc: dropout epilogue needs N%%4==0");
@@ -410,6 +446,7 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
   for (int i = 0; i < PKA_MAX_CTX; ++i) p.shift[i] = d->shift[i];
   p.C = d->C; p.Ct = d->Ct; p.ldc = d->ldc; p.c_dtype = d->c_dtype; p.Tp = d->Tp;
   p.bias = d->bias; p.relu = d->relu; p.M = d->M; p.drop = d->drop;
+  p.addend = d->mode == 0 ? (const __nv_bfloat16*)d->addend : nullptr; p.ld_add = d->ldadd;
   p.kb_per_seg = (d->K + TC_BK - 1) / TC_BK;
   p.tiles_per_utt = (d->T + TC_BM - 1) / TC_BM;
   p.utt_per_split = 0; p.tb_per_utt = 0;
@@ -455,6 +492,56 @@ extern "C" int pka_gemm_tc(const pka_tc_desc* d, void* stream) {
   }
   launch_k(gemm_tc_kernel, grid, TC_THREADS, TC_SMEM, as_stream(stream), mapA, mapB, p);
   return check_launch("gemm_tc");
+}
+
+// Weight gradients (mode 2) of several independent problems in one launch (see gemm_tc_group_kernel).  Every descriptor
+// is what pka_gemm_tc would take; problems the CTA-pair kernel would handle are accepted too (they run on this kernel).
+extern "C" int pka_gemm_tc_wgrad_group(const pka_tc_desc* descs, int n_desc, void* stream) {
+  PKA_REQUIRE(descs && n_desc > 0, PKA_EINVAL, "gemm_tc_wgrad_group: empty table");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "gemm_tc_wgrad_group: cannot opt in to %d bytes of shared memory: %s", TC_SMEM, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int dbg = 0;
+  { const char* e = getenv("PKA_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  for (int base = 0; base < n_desc; base += TC_GROUP) {
+    static thread_local TcGroup g;                 // 20 KB: keep it off the stack
+    const int n = n_desc - base < TC_GROUP ? n_desc - base : TC_GROUP;
+    int ctas = 0;
+    for (int i = 0; i < n; ++i) {
+      const pka_tc_desc* d = descs + base + i;
+      PKA_REQUIRE(d->A && d->B && d->C && d->mode == 2, PKA_EINVAL, "gemm_tc_wgrad_group: problem %d: mode-2 descriptor with operands expected", base + i);
+      PKA_REQUIRE(d->Bt > 0 && d->T > 0 && d->M > 0 && d->N > 0 && d->nseg >= 1 && d->nseg <= PKA_MAX_CTX && d->splits >= 1 && d->c_dtype == PKA_F32,
+                  PKA_EINVAL, "gemm_tc_wgrad_group: problem %d: bad sizes", base + i);
+      TcParams& p = g.p[i];
+      p.mode = 2; p.Bt = d->Bt; p.T = d->T; p.N = d->N; p.K = d->K; p.nseg = d->nseg;
+      p.a_seg_col = d->a_seg_col; p.b_seg_col = d->b_seg_col;
+      for (int k = 0; k < PKA_MAX_CTX; ++k) p.shift[k] = d->shift[k];
+      p.C = d->C; p.Ct = nullptr; p.ldc = d->ldc; p.c_dtype = d->c_dtype; p.Tp = 0;
+      p.bias = nullptr; p.relu = 0; p.M = d->M; p.drop = no_dropout(); p.addend = nullptr; p.ld_add = 0;
+      p.kb_per_seg = (d->K + TC_BK - 1) / TC_BK;
+      p.tiles_per_utt = (d->T + TC_BM - 1) / TC_BM;
+      p.utt_per_split = (d->Bt + d->splits - 1) / d->splits;
+      p.tb_per_utt = (d->T + TC_BK - 1) / TC_BK;
+      p.dbg = dbg;
+      int rc = make_map(&g.mapA[i], d->A, d->M, d->T, d->Bt, (uint64_t)d->lda * 2, (uint64_t)d->T * d->lda * 2, 64, 1, "gemm_tc_wgrad_group dZ");
+      if (rc) return rc;
+      rc = make_map(&g.mapB[i], d->B, d->N, d->T, d->Bt, (uint64_t)d->ldb * 2, (uint64_t)d->T * d->ldb * 2, 64, 1, "gemm_tc_wgrad_group X");
+      if (rc) return rc;
+      g.gx[i] = (d->M + TC_BM - 1) / TC_BM;
+      g.gy[i] = ((d->N + TC_BN - 1) / TC_BN) * d->nseg;
+      g.cta_start[i] = ctas;
+      ctas += g.gx[i] * g.gy[i] * d->splits;
+    }
+    g.cta_start[n] = ctas;
+    g.n = n;
+    launch_k(gemm_tc_group_kernel, ctas, TC_THREADS, TC_SMEM, as_stream(stream), g);
+    int rc = check_launch("gemm_tc_wgrad_group");
+    if (rc) return rc;
+  }
+  return PKA_OK;
 }
 
 extern "C" int pka_tc_reduce(const float* ws, float* out, int64_t per, int splits, int accumulate, void* stream) {

@@ -41,6 +41,7 @@ struct Rows2Params {
   void* C; int ldc, c_dtype;
   const float* bias; int relu;
   pka_dropout drop;
+  const __nv_bfloat16* addend; int ld_add;       // optional: C = epi(acc) + addend[m, n]  (residual-gradient branch)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -348,6 +349,21 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] * dc.scale : 0.f;
           }
           ++kw;
+          if (p.addend && valid && nb < p.N) {     // + residual-gradient branch (bf16 row segment of this thread's row)
+            const __nv_bfloat16* ar = p.addend + m * p.ld_add + nb;
+            if (nb + 32 <= p.N && (p.ld_add & 7) == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 a4 = *reinterpret_cast<const uint4*>(ar + g * 8);
+                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(ah[k]); v[g * 8 + 2 * k] += f.x; v[g * 8 + 2 * k + 1] += f.y; }
+              }
+            } else {
+#pragma unroll 4
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __bfloat162float(ar[j]);
+            }
+          }
           if (p.tma_store) {                       // bf16 row segment -> swizzled staging tile (conflict-free 16 B stores)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -499,6 +515,7 @@ int launch_rows2(const pka_tc_desc* d, cudaStream_t st, bool* handled) {
   { const char* e = getenv("PKA_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("PKA_TC_BASEOFF"); p.use_base_offset = e ? atoi(e) : 0; }     // diagnostics only, see header
   p.C = d->C; p.ldc = d->ldc; p.c_dtype = d->c_dtype; p.bias = d->bias; p.relu = d->relu; p.drop = d->drop;
+  p.addend = (const __nv_bfloat16*)d->addend; p.ld_add = d->ldadd;
   p.tma_store = (d->c_dtype == PKA_BF16 && d->ldc % 8 == 0 && aligned16(d->C)) ? 1 : 0;
   if (const char* e = getenv("PKA_TC_TMASTORE")) p.tma_store = p.tma_store && atoi(e) != 0;
   CUtensorMap mapA, mapB, mapC;

@@ -130,14 +130,14 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
                   T* __restrict__ dx, T* __restrict__ dres, float* __restrict__ dab_ws, int rows, int D, float eps,
                   const pka_dropout drop) {
   pdl_wait();
-  __shared__ float red[kLnWarps][2][32 * EV * VPL];
+  __shared__ float red[kLnWarps][3][32 * EV * VPL];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DropCtx dc = make_drop(drop);
-  float da_acc[VPL][EV], db_acc[VPL][EV];
+  float da_acc[VPL][EV], db_acc[VPL][EV], dxs_acc[VPL][EV];       // dxs: column sums of the dx this kernel writes
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
 #pragma unroll
-    for (int i = 0; i < EV; ++i) { da_acc[v][i] = 0.f; db_acc[v][i] = 0.f; }
+    for (int i = 0; i < EV; ++i) { da_acc[v][i] = 0.f; db_acc[v][i] = 0.f; dxs_acc[v][i] = 0.f; }
   }
 
   for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
@@ -201,6 +201,9 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
           for (int i = 0; i < EV; ++i) dz[i] *= keep[v][i];
           stv<T, EV>(dx + (long long)row * D + col, dz);
         }
+        // bias gradient of the linear layer below = column sums of exactly what it will read (the stored, rounded dx)
+#pragma unroll
+        for (int i = 0; i < EV; ++i) dxs_acc[v][i] += to_f(from_f<T>(dz[i]));
       }
     }
   }
@@ -209,15 +212,15 @@ add_ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __
   for (int v = 0; v < VPL; ++v) {
     const int col = (v * 32 + lane) * EV;
 #pragma unroll
-    for (int i = 0; i < EV; ++i) { red[warp][0][col + i] = da_acc[v][i]; red[warp][1][col + i] = db_acc[v][i]; }
+    for (int i = 0; i < EV; ++i) { red[warp][0][col + i] = da_acc[v][i]; red[warp][1][col + i] = db_acc[v][i]; red[warp][2][col + i] = dxs_acc[v][i]; }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * D; e += kLnWarps * 32) {
+  for (int e = threadIdx.x; e < 3 * D; e += kLnWarps * 32) {
     const int which = e / D, col = e % D;
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kLnWarps; ++w) s += red[w][which][col];
-    dab_ws[((long long)blockIdx.x * 2 + which) * D + col] = s;
+    dab_ws[((long long)blockIdx.x * 3 + which) * D + col] = s;      // per CTA: [da | db | colsum(dx)]
   }
 }
 
@@ -235,9 +238,9 @@ ln_dab_finish_kernel(const float* __restrict__ ws, float* __restrict__ da, float
     int b = w;
     for (; b + 24 < nblk; b += 32) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) s[u] += ws[((long long)(b + 8 * u) * 2 + which) * D + col];
+      for (int u = 0; u < 4; ++u) s[u] += ws[((long long)(b + 8 * u) * 3 + which) * D + col];
     }
-    for (; b < nblk; b += 8) s[0] += ws[((long long)b * 2 + which) * D + col];
+    for (; b < nblk; b += 8) s[0] += ws[((long long)b * 3 + which) * D + col];
   }
   red[w][lane] = (s[0] + s[1]) + (s[2] + s[3]);
   __syncthreads();
@@ -283,7 +286,7 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
   }
 #undef LN_BWD
   int rc = check_launch("add_layernorm_bwd");
-  if (rc) return rc;
+  if (rc || (!da && !db)) return rc;               // no da/db: the caller finishes the partial rows (pka_reduce_jobs)
   launch_k(ln_dab_finish_kernel, 2 * ((D + 31) / 32), 256, 0, st, ws, da, db, nblk, D);
   return check_launch("ln_dab_finish");
 }
@@ -293,7 +296,9 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
 extern "C" int pka_ln_bwd_blocks(int rows) {
   int need = (rows + pka::kLnWarps - 1) / pka::kLnWarps;
   // few partial rows keep the fixed-order finish short (small decoder tensors); one CTA per SM for large ones
-  int cap = rows <= 8192 ? 64 : pka::kNumSMs * 8;  // enough resident warps to pull HBM bandwidth on large tensors
+  // one row per warp for the small decoder tensors (a warp walks its rows serially: 4 rows = 4 dependent round trips
+  // to L2); the partial rows are summed by the batched reduction launch, so their number no longer costs a kernel
+  int cap = rows <= 8192 ? 256 : pka::kNumSMs * 8; // enough resident warps to pull HBM bandwidth on large tensors
   return need < cap ? (need > 0 ? need : 1) : cap;
 }
 
@@ -315,7 +320,7 @@ extern "C" int pka_add_layernorm_bwd(const void* dy, const void* x, const void* 
                                      float* dab_ws, int dtype, int rows, int D, float eps, const pka_dropout* drop,
                                      void* stream) {
   using namespace pka;
-  PKA_REQUIRE(dy && x && a && mean && rinv && da && db && dab_ws && (dx || dres), PKA_EINVAL, "add_layernorm_bwd: null pointer");
+  PKA_REQUIRE(dy && x && a && mean && rinv && ((da && db) || (!da && !db)) && dab_ws && (dx || dres), PKA_EINVAL, "add_layernorm_bwd: null pointer");
   PKA_REQUIRE(rows > 0 && D >= 4 && D % 4 == 0 && D <= 512, PKA_EUNSUPPORTED, "add_layernorm_bwd: rows=%d D=%d (need D%%4==0, 4<=D<=512)", rows, D);
   PKA_REQUIRE(aligned16(a) && aligned16(x) && aligned16(dy) && (!dx || aligned16(dx)) && (!dres || aligned16(dres)) && (!residual || aligned16(residual)), PKA_EALIGN, "add_layernorm_bwd: pointers must be 16-byte aligned");
   pka_dropout dr = drop ? *drop : no_dropout();

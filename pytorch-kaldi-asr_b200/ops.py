@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
+import threading
 from typing import Optional, Sequence
 
 import torch
@@ -123,15 +125,101 @@ def grad_buffer(param_like: torch.Tensor, shape=None) -> torch.Tensor:
     return torch.empty(shape, device=param_like.device, dtype=torch.float32)
 
 
-def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: Optional[bool] = None) -> torch.Tensor:
+# ------------------------------------------------------------------------------------------------ deferred work
+# The TIMIT-config step is launch bound.  Two kinds of backward work are NOT on the critical
+# path of the backward pass -- nothing reads their result before the optimiser (or the gradient all-reduce) does:
+#   * the fixed-order sums of split partials (weight-gradient splits, bias / LayerNorm column sums, packed per-head
+#     gradients): round 1 ran 57 small "finish" kernels per step;
+#   * the decoder-shaped weight gradients themselves (a few output tiles each, ~6 us per launch, 23 per step).
+# Backward functions therefore only *record* them; one grouped weight-gradient launch and one reduction launch run at the
+# end of the backward pass (autograd engine callback), or earlier when a data-parallel gradient bucket is about to leave.
+# Summation orders are unchanged (bit-reproducible).  PKA_DEFER=0 restores one launch per reduction.
+DEFER_ENABLED = os.environ.get("PKA_DEFER", "1") != "0"
+
+
+class _Deferred:
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.wgrads, self.jobs, self.keep, self.queued = [], [], [], False
+
+
+_DEFER = _Deferred()
+
+
+def _defer_schedule() -> bool:
+    """True if work recorded now will be flushed by the running backward pass (callback installed); False when deferral
+    is off or we are not inside a backward pass (the caller then finishes its reductions itself)."""
+    if not DEFER_ENABLED:
+        return False
+    d = _DEFER
+    if d.queued:
+        return True
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(flush_deferred)
+    except RuntimeError:
+        return False
+    d.queued = True
+    return True
+
+
+def defer_reduce(src: torch.Tensor, dst: torch.Tensor, n: int, splits: int, split_stride: int, *, src_off: int = 0,
+                 kind: int = L.REDUCE_PLAIN, accumulate: bool = False, D: int = 0, dk: int = 0):
+    """Record dst[...] (+)= sum_s src[src_off + s*split_stride + e] for pka_reduce_jobs; `src` is kept alive until the flush."""
+    j = L.ReduceJob()
+    j.src, j.dst = src.data_ptr() + 4 * src_off, dst.data_ptr()
+    j.n, j.split_stride, j.splits, j.kind, j.accumulate, j.D, j.dk = n, split_stride, splits, kind, int(accumulate), D, dk
+    # only the partials are kept alive: `dst` is a gradient tensor autograd is about to adopt, and an extra reference
+    # would make AccumulateGrad clone it (before the sum has been written) instead of taking it over
+    with _DEFER.lock:
+        _DEFER.jobs.append(j)
+        _DEFER.keep.append(src)
+
+
+def flush_deferred():
+    """Launch everything recorded so far: first the grouped weight gradients (their partials feed the sums), then the
+    reductions.  Called by the autograd engine at the end of a backward pass, by parallel.GradAllReduce before a bucket
+    leaves, and defensively by FusedAdam.step()."""
+    d = _DEFER
+    with d.lock:
+        wg, jobs, keep = d.wgrads, d.jobs, d.keep
+        d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
+    if wg:
+        arr = (L.TcDesc * len(wg))(*wg)
+        L.check(L.lib().pka_gemm_tc_wgrad_group(arr, len(wg), L.stream_ptr()), "gemm_tc_wgrad_group")
+    if jobs:
+        arr = (L.ReduceJob * len(jobs))(*jobs)
+        L.check(L.lib().pka_reduce_jobs(arr, len(jobs), L.stream_ptr()), "reduce_jobs")
+    del keep
+
+
+def reset_deferred():
+    """Drop anything a failed backward pass may have left behind (called at the start of a forward pass)."""
+    d = _DEFER
+    with d.lock:
+        d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
+    _COLSUM_HINTS.clear()
+
+
+# LayerNorm backward also leaves the column sums of the gradient it hands to the layer below (its dx) as partial rows in
+# its workspace: when that layer is a bias-carrying linear map fed by exactly this tensor, its bias gradient is those
+# sums -- no separate column-sum pass over dx.  Keyed by the address of dx; cleared at every forward pass.
+_COLSUM_HINTS = {}
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: Optional[bool] = None,
+           defer: bool = False) -> torch.Tensor:
     rows, n = x2d.shape
     acc = (out is not None) if accumulate is None else bool(accumulate)
     if out is None:
         out = torch.empty(n, device=x2d.device, dtype=torch.float32)
     chunks = L.lib().pka_colsum_chunks(C.c_int64(rows))
     ws = torch.empty(chunks * n, device=x2d.device, dtype=torch.float32)
-    L.check(L.lib().pka_colsum(L.ptr(x2d), L.ptr(out), L.ptr(ws), L.dtype_code(x2d), C.c_int64(rows), n, x2d.stride(0),
-                               int(acc), L.stream_ptr()), "colsum")
+    deferred = defer and _defer_schedule()
+    L.check(L.lib().pka_colsum(L.ptr(x2d), C.c_void_p(0) if deferred else L.ptr(out), L.ptr(ws), L.dtype_code(x2d),
+                               C.c_int64(rows), n, x2d.stride(0), int(acc), L.stream_ptr()), "colsum")
+    if deferred:
+        parts = L.lib().pka_colsum_parts(L.ptr(x2d), L.ptr(ws), L.dtype_code(x2d), C.c_int64(rows), n, x2d.stride(0))
+        defer_reduce(ws, out, n, parts, n, accumulate=acc)
     return out
 
 
@@ -249,10 +337,12 @@ class _HeadProjFn(torch.autograd.Function):
     Replaces q.repeat(n_head)+bmm (T/SubLayers.py:49-56): no replication, heads are column blocks."""
 
     @staticmethod
-    def forward(ctx, x, *ws):
+    def forward(ctx, x, link, *ws):
         L.require_cuda(x, *ws)
         if x.dtype == torch.bfloat16:
-            return _HeadProjFn._forward_tc(ctx, x, ws)
+            return _HeadProjFn._forward_tc(ctx, x, ws, link)
+        if link is not None:
+            link.armed = False
         ctx.tc = False
         lead, D = x.shape[:-1], x.shape[-1]
         x2 = x.reshape(-1, D)
@@ -271,7 +361,7 @@ class _HeadProjFn(torch.autograd.Function):
         return out.view(*lead, P * H * dk)
 
     @staticmethod
-    def _forward_tc(ctx, x, ws):
+    def _forward_tc(ctx, x, ws, link=None):
         """bf16 x [Bt,T,D]: one tcgen05 GEMM for all P*H heads; the packed q|k|v (or k|v) buffer stays bf16 because its
         only consumer is the tensor-core attention kernel."""
         assert x.dim() == 3 and x.is_contiguous()
@@ -280,11 +370,17 @@ class _HeadProjFn(torch.autograd.Function):
         P = len(ws)
         ntot = P * H * dk
         needs_dx = ctx.needs_input_grad[0]
-        wf = torch.empty(ntot, D, device=x.device, dtype=torch.bfloat16)
-        wd = torch.empty(D, ntot, device=x.device, dtype=torch.bfloat16) if needs_dx else None
-        wp = [L.ptr(w.detach()) for w in ws] + [C.c_void_p(0)] * (3 - P)
-        L.check(L.lib().pka_head_weight_relayout(wp[0], wp[1], wp[2], P, H, D, dk, L.ptr(wf), L.ptr(wd), L.stream_ptr()),
-                "head_weight_relayout")
+        if OPERANDS is not None and all(w.is_contiguous() for w in ws):
+            wf, wd = OPERANDS.heads(ws)                             # refreshed once per forward pass, not per op
+        else:
+            wf = torch.empty(ntot, D, device=x.device, dtype=torch.bfloat16)
+            wd = torch.empty(D, ntot, device=x.device, dtype=torch.bfloat16) if needs_dx else None
+            wp = [L.ptr(w.detach()) for w in ws] + [C.c_void_p(0)] * (3 - P)
+            L.check(L.lib().pka_head_weight_relayout(wp[0], wp[1], wp[2], P, H, D, dk, L.ptr(wf), L.ptr(wd), L.stream_ptr()),
+                    "head_weight_relayout")
+        if link is not None:
+            link.armed = bool(needs_dx)
+        ctx.link = link if (link is not None and link.armed) else None
         out = gemm_tc_rows(x, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.bfloat16)
         ctx.tc = True
         ctx.save_for_backward(x, wd, *ws)
@@ -298,16 +394,14 @@ class _HeadProjFn(torch.autograd.Function):
         ntot = P * H * dk
         dz = dy if (dy.dtype == torch.bfloat16 and dy.is_contiguous()) else gate_to_bf16(dy, Bt, T, ntot)
         dx = None
+        addend = ctx.link.take() if ctx.link is not None else None       # residual-branch gradient of the sub-layer input
         if ctx.needs_input_grad[0]:
-            dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot)
+            dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot, addend=addend)
         dws = [None] * P
-        if any(ctx.needs_input_grad[1:1 + P]):
-            part, splits = gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,), reduce=False)
-            dws = [grad_buffer(ws[p]) if ctx.needs_input_grad[1 + p] else None for p in range(P)]
-            gp = [L.ptr(g) for g in dws] + [C.c_void_p(0)] * (3 - P)
-            L.check(L.lib().pka_tc_reduce_heads(L.ptr(part), gp[0], gp[1], gp[2], splits, P, H, D, dk, L.stream_ptr()),
-                    "tc_reduce_heads")
-        return (dx, *dws)
+        if any(ctx.needs_input_grad[2:2 + P]):
+            dws = [grad_buffer(ws[p]) if ctx.needs_input_grad[2 + p] else None for p in range(P)]
+            gemm_tc_wgrad(dz, x, Bt, T, ntot, D, 1, (0,), defer=True, heads=(dws, P, H, D, dk))
+        return (dx, None, *dws)
 
     @staticmethod
     def backward(ctx, dy):
@@ -329,7 +423,7 @@ class _HeadProjFn(torch.autograd.Function):
             dx = dx.view(*lead, D)
         dws = []
         for p, w in enumerate(ws):
-            if not ctx.needs_input_grad[1 + p]:
+            if not ctx.needs_input_grad[2 + p]:
                 dws.append(None)
                 continue
             dw = grad_buffer(w)
@@ -337,11 +431,11 @@ class _HeadProjFn(torch.autograd.Function):
             gemm(x2, dy2, dw, D, dk, M, nbatch=H, lda=D, ldb=P * H * dk, ldc=dk, transA=True, transB=False,
                  b_batch_off=dk, c_batch_off=D * dk, b_ptr_off=p * H * dk)
             dws.append(dw)
-        return (dx, *dws)
+        return (dx, None, *dws)
 
 
-def head_proj(x, *ws):
-    return _HeadProjFn.apply(x, *ws)
+def head_proj(x, *ws, link: Optional[ResidualLink] = None):
+    return _HeadProjFn.apply(x, link, *ws)
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -351,6 +445,7 @@ class _AttnFn(torch.autograd.Function):
         """self-attention: qbuf = packed [B,L,3*H*dk] (q|k|v), kvbuf None.
         cross-attention: qbuf = [B,Lq,H*dk], kvbuf = packed [B,Lk,2*H*dk] (k|v)."""
         L.require_cuda(qbuf, kvbuf, key_mask)
+        ctx.set_materialize_grads(False)          # no zero-filled gradients for the statistics outputs
         qbuf = qbuf.contiguous()
         HD = H * dk
         B, Lq = qbuf.shape[0], qbuf.shape[1]
@@ -384,6 +479,8 @@ class _AttnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dlse, _dprobs):
+        if dout is None:
+            return (None,) * 9
         qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
         d = ctx.desc
         HD = d.H * d.dk
@@ -411,6 +508,7 @@ class _AttnTcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qbuf, kvbuf, key_mask, H, dk, band, scale, drop, out_fp32):
         L.require_cuda(qbuf, kvbuf, key_mask)
+        ctx.set_materialize_grads(False)          # no zero-filled gradient for the lse output
         assert qbuf.dtype == torch.bfloat16 and (kvbuf is None or kvbuf.dtype == torch.bfloat16)
         qbuf = qbuf.contiguous()
         HD = H * dk
@@ -442,6 +540,8 @@ class _AttnTcFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dlse):
+        if dout is None:
+            return (None,) * 9
         qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
         d = ctx.desc
         HD = d.H * d.dk
@@ -484,9 +584,27 @@ def attention_tc(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: floa
 
 
 # ------------------------------------------------------------------------------------------------ add + LayerNorm
+class ResidualLink:
+    """Side channel between the two backward functions of a post-LN sub-layer  y = LN(f(x) + x).
+
+    Autograd would add the two gradient branches of x (through f and through the residual) with an element-wise kernel
+    of its own.  Here the LayerNorm backward (which runs first) hands its residual-branch gradient over through this
+    object instead of returning it, and the FIRST op of f (a tensor-core projection) adds it in the epilogue of its
+    data-gradient GEMM: dX = dZ.W + dResidual, one launch and one pass less per sub-layer.  `armed` is set by the
+    consuming op in its forward when it will really produce dX on the tensor-core path."""
+    __slots__ = ("armed", "dres")
+
+    def __init__(self):
+        self.armed, self.dres = False, None
+
+    def take(self):
+        d, self.dres = self.dres, None
+        return d
+
+
 class _AddLayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, a, b, eps, drop):
+    def forward(ctx, x, residual, a, b, eps, drop, link=None):
         L.require_cuda(x, residual, a, b)
         shape = x.shape
         D = shape[-1]
@@ -501,6 +619,7 @@ class _AddLayerNormFn(torch.autograd.Function):
                 "add_layernorm_fwd")
         ctx.save_for_backward(x2, r2, a, mean, rinv, b)
         ctx.meta = (shape, eps, drop)
+        ctx.link = link if (link is not None and link.armed and r2 is not None) else None
         return y.view(shape)
 
     @staticmethod
@@ -514,18 +633,34 @@ class _AddLayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x2) if use_drop else None
         da, db = grad_buffer(a), grad_buffer(b_par)                 # overwritten by the kernel
         nblk = L.lib().pka_ln_bwd_blocks(rows)
-        ws = torch.empty(2 * D * nblk, device=dy.device, dtype=torch.float32)
+        ws = torch.empty(3 * D * nblk, device=dy.device, dtype=torch.float32)    # per CTA: [da | db | column sums of dx]
+        deferred = _defer_schedule()                                # the gain / offset partial rows are summed at the flush
+        null = C.c_void_p(0)
         L.check(L.lib().pka_add_layernorm_bwd(L.ptr(dy2), L.ptr(x2), L.ptr(r2), L.ptr(a), L.ptr(mean), L.ptr(rinv), L.ptr(dx),
-                                              L.ptr(dres), L.ptr(da), L.ptr(db), L.ptr(ws), L.dtype_code(x2), rows, D,
+                                              L.ptr(dres), null if deferred else L.ptr(da), null if deferred else L.ptr(db),
+                                              L.ptr(ws), L.dtype_code(x2), rows, D,
                                               C.c_float(eps), _byref_drop(drop), L.stream_ptr()), "add_layernorm_bwd")
+        if deferred:
+            defer_reduce(ws, da, D, nblk, 3 * D)
+            defer_reduce(ws, db, D, nblk, 3 * D, src_off=D)
         dres_v = dres.view(shape)
         dx_v = dx.view(shape) if use_drop else dres_v
-        return dx_v, (dres_v if r2 is not None else None), da, db, None, None
+        if deferred:
+            _COLSUM_HINTS[dx_v.data_ptr()] = (ws, nblk, rows, D)
+        if ctx.link is not None:                  # the residual branch travels to the sub-layer's first GEMM (see ResidualLink)
+            if use_drop:
+                ctx.link.dres = dres_v
+                return dx_v, None, da, db, None, None, None
+            # without dropout dx and dres are ONE buffer: it must stay intact for the projection's backward, so the
+            # consumer reads it as the addend and this branch returns it as is
+            ctx.link.dres = dres_v
+            return dx_v, None, da, db, None, None, None
+        return dx_v, (dres_v if r2 is not None else None), da, db, None, None, None
 
 
-def add_layer_norm(x, residual, a, b, eps: float = 1e-3, drop: Optional[Drop] = None):
+def add_layer_norm(x, residual, a, b, eps: float = 1e-3, drop: Optional[Drop] = None, link: Optional[ResidualLink] = None):
     """LayerNormalization(dropout(x) + residual) with the reference's formula (T/Modules.py:42-51)."""
-    return _AddLayerNormFn.apply(x, residual, a, b, eps, drop)
+    return _AddLayerNormFn.apply(x, residual, a, b, eps, drop, link)
 
 
 # ------------------------------------------------------------------------------------------------ embedding, positions
@@ -627,11 +762,16 @@ def add_pos_dropout(x, pos_table: Optional[torch.Tensor], drop: Optional[Drop] =
 class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits2d, goal, smoothing, eps):
-        L.require_cuda(logits2d, goal)
+        out3 = _CE_OUT.pop() if _CE_OUT else None          # caller-owned result buffer (not an autograd input)
+        L.require_cuda(logits2d, goal, out3)
+        ctx.set_materialize_grads(False)
         logits2d = logits2d.contiguous()
         goal = goal.to(torch.int64).contiguous()
         N, V = logits2d.shape
-        out3 = torch.empty(3, device=logits2d.device, dtype=torch.float32)
+        if out3 is None:
+            out3 = torch.empty(3, device=logits2d.device, dtype=torch.float32)
+        else:
+            assert out3.dtype == torch.float32 and out3.numel() == 3 and out3.is_contiguous()
         lse = torch.empty(N, device=logits2d.device, dtype=torch.float32)
         nblk = L.lib().pka_ce_blocks(N)
         ws = torch.empty(3 * nblk, device=logits2d.device, dtype=torch.float32)
@@ -646,6 +786,8 @@ class _CrossEntropyFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, _gstats):
+        if gloss is None:
+            return None, None, None, None
         logits2d, goal, lse = ctx.saved_tensors
         smoothing, eps = ctx.meta
         N, V = logits2d.shape
@@ -656,9 +798,33 @@ class _CrossEntropyFn(torch.autograd.Function):
         return dl, None, None, None
 
 
-def cross_entropy_sum(logits2d, goal, smoothing: bool = False, eps: float = 0.1):
-    """-> (loss_sum scalar tensor, stats tensor [n_correct, n_words]); PAD (=0) targets ignored (L/train.py:58-90)."""
-    return _CrossEntropyFn.apply(logits2d, goal, bool(smoothing), float(eps))
+_CE_OUT = []
+
+
+def cross_entropy_sum(logits2d, goal, smoothing: bool = False, eps: float = 0.1, out3: Optional[torch.Tensor] = None):
+    """-> (loss_sum scalar tensor, stats tensor [n_correct, n_words]); PAD (=0) targets ignored (L/train.py:58-90).
+    `out3`: caller-owned float[3] the kernel writes {loss, n_correct, n_words} into (the results are views of it)."""
+    if out3 is not None:
+        _CE_OUT.append(out3)
+    try:
+        return _CrossEntropyFn.apply(logits2d, goal, bool(smoothing), float(eps))
+    finally:
+        _CE_OUT.clear()
+
+
+def split_targets(tgt: torch.Tensor, tgt_pad_mask: torch.Tensor):
+    """Teacher-forcing split of L/train.py:163-165 in one launch: -> (tgt[:, :-1], tgt[:, 1:], mask[:, :-1]) as
+    contiguous tensors (the three strided views would otherwise each be copied by the op that consumes them)."""
+    L.require_cuda(tgt, tgt_pad_mask)
+    tgt = tgt.to(torch.int64).contiguous()
+    mask = tgt_pad_mask.to(torch.uint8).contiguous()
+    B, L1 = tgt.shape
+    tgt_in = torch.empty(B, L1 - 1, device=tgt.device, dtype=torch.int64)
+    goal = torch.empty(B, L1 - 1, device=tgt.device, dtype=torch.int64)
+    mask_in = torch.empty(B, L1 - 1, device=tgt.device, dtype=torch.uint8)
+    L.check(L.lib().pka_split_targets(L.ptr(tgt), L.ptr(mask), L.ptr(tgt_in), L.ptr(goal), L.ptr(mask_in), B, L1,
+                                      L.stream_ptr()), "split_targets")
+    return tgt_in, goal, mask_in
 
 
 # ------------------------------------------------------------------------------------------------ test helper
@@ -676,11 +842,111 @@ def attn_keep_mask(B: int, H: int, Lq: int, Lk: int, drop: Drop, device) -> torc
     return dropout_keep_mask(B * H * Lq * Lk8, drop, device).view(B, H, Lq, Lk8)[..., :Lk].contiguous()
 
 
+# ================================================================================================ operand cache
+class OperandCache:
+    """bf16 GEMM operand copies of a model's fp32 master weights, refreshed by ONE launch per forward pass.
+
+    The tensor-core GEMMs read the weights as bf16 in two layouts (forward: nn.Linear layout; data-gradient: transposed
+    per splice segment; per-head projection tensors packed as q|k|v column blocks).  Round 1 rebuilt them inside every
+    op (29 small launches per step).  Entries register themselves the first time an op sees a weight while this cache
+    is active (one-off relayout with the stand-alone kernels); from then on `refresh()` rewrites all of them with
+    pka_relayout_jobs -- the weights only change in the optimiser step -- and, when asked, advances the dropout step
+    counter in the same launch.  Entries follow their parameter if its storage moves (FusedAdam arena, .to())."""
+
+    def __init__(self):
+        self.entries = {}            # key (storage addresses) -> dict(params, wf, wd, spec, seen)
+        self._table = None           # ctypes array, rebuilt when the set of entries changes
+        self._n = 0
+        self.epoch = 0               # forward passes seen; entries a whole pass did not touch are dropped (moved weights)
+
+    # -- registration (first use)
+    def plain(self, weight, N, K, nseg):
+        key = ("w", weight.data_ptr(), N, K, nseg)
+        ent = self.entries.get(key)
+        if ent is not None:
+            ent["seen"] = self.epoch
+        if ent is None:
+            dev = weight.device
+            ent = dict(params=[weight], wf=torch.empty(N, nseg * K, device=dev, dtype=torch.bfloat16),
+                       wd=torch.empty(K, nseg * N, device=dev, dtype=torch.bfloat16),
+                       spec=[(L.RELAYOUT_PLAIN, N, K, nseg, nseg * K, nseg * N, 0)], seen=self.epoch)
+            self.entries[key] = ent
+            self._table = None
+            self._relayout_now(ent)
+        return ent["wf"], ent["wd"]
+
+    def heads(self, ws):
+        """Packed operand of the per-head tensors `ws` (each [H, D, dk]): wf [(p,h,j), d], wd [d, (p,h,j)]."""
+        key = ("h",) + tuple(w.data_ptr() for w in ws) + tuple(ws[0].shape)
+        ent = self.entries.get(key)
+        if ent is not None:
+            ent["seen"] = self.epoch
+        if ent is None:
+            H, D, dk = ws[0].shape
+            ntot = len(ws) * H * dk
+            dev = ws[0].device
+            ent = dict(params=list(ws), wf=torch.empty(ntot, D, device=dev, dtype=torch.bfloat16),
+                       wd=torch.empty(D, ntot, device=dev, dtype=torch.bfloat16),
+                       spec=[(L.RELAYOUT_HEADS, H, D, dk, D, ntot, p_ * H * dk) for p_ in range(len(ws))], seen=self.epoch)
+            self.entries[key] = ent
+            self._table = None
+            self._relayout_now(ent)
+        return ent["wf"], ent["wd"]
+
+    def _jobs_of(self, ent):
+        jobs = []
+        for w, (kind, N, K, nseg, ldf, ldd, n0) in zip(ent["params"], ent["spec"]):
+            if not w.is_contiguous() or w.dtype != torch.float32:
+                raise RuntimeError("OperandCache: fp32 contiguous master weights expected")
+            j = L.RelayoutJob()
+            j.src, j.wf, j.wd = w.data_ptr(), ent["wf"].data_ptr(), ent["wd"].data_ptr()
+            j.N, j.K, j.nseg, j.kind, j.ldf, j.ldd, j.n0 = N, K, nseg, kind, ldf, ldd, n0
+            jobs.append(j)
+        return jobs
+
+    def _relayout_now(self, ent):
+        jobs = self._jobs_of(ent)
+        arr = (L.RelayoutJob * len(jobs))(*jobs)
+        L.check(L.lib().pka_relayout_jobs(arr, len(jobs), C.c_void_p(0), L.stream_ptr()), "relayout_jobs")
+
+    # -- once per forward pass
+    def refresh(self, step_counter: Optional[torch.Tensor] = None):
+        """Rewrite every registered operand copy from its master weight (one launch); `step_counter`: the model's dropout
+        step counter, advanced by one in the same launch."""
+        stale = [k for k, ent in self.entries.items() if ent["seen"] < self.epoch]
+        if stale and self.epoch > 0:                  # weights that moved (or left the model) since the last pass
+            for k in stale:
+                del self.entries[k]
+            self._table = None
+        self.epoch += 1
+        if self._table is None:
+            jobs = [j for ent in self.entries.values() for j in self._jobs_of(ent)]
+            self._table = (L.RelayoutJob * max(1, len(jobs)))(*jobs)
+            self._n = len(jobs)
+        L.check(L.lib().pka_relayout_jobs(self._table, self._n, L.ptr(step_counter), L.stream_ptr()), "relayout_jobs")
+
+    def active(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            global OPERANDS
+            prev, OPERANDS = OPERANDS, self
+            try:
+                yield self
+            finally:
+                OPERANDS = prev
+        return cm()
+
+
+OPERANDS: Optional[OperandCache] = None      # set by Transformer.forward around the bf16 path
+
+
 # ================================================================================================ bf16 tensor-core path
 def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col=0, shift=(), bias=None, relu=False,
-                 drop: Optional[Drop] = None, out_dtype=torch.bfloat16):
-    """mode 0 of pka_gemm_tc: C[b,t,:] = epi(sum_seg A[b,t+shift[seg],:] . Bw[:, seg]^T) -> C [Bt,T,N]."""
-    L.require_cuda(A, Bw, bias)
+                 drop: Optional[Drop] = None, out_dtype=torch.bfloat16, addend=None):
+    """mode 0 of pka_gemm_tc: C[b,t,:] = epi(sum_seg A[b,t+shift[seg],:] . Bw[:, seg]^T) [+ addend] -> C [Bt,T,N]."""
+    L.require_cuda(A, Bw, bias, addend)
     assert A.dtype == torch.bfloat16 and Bw.dtype == torch.bfloat16
     Cout = torch.empty(Bt, T, N, device=A.device, dtype=out_dtype)
     d = L.TcDesc()
@@ -693,16 +959,25 @@ def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col
         d.shift[i] = int(sft)
     d.relu, d.c_dtype, d.splits = int(relu), L.dtype_code(Cout), 1
     d.drop = _cdrop(drop)
+    if addend is not None:
+        assert addend.dtype == torch.bfloat16 and addend.is_contiguous() and addend.numel() == Bt * T * N
+        d.addend, d.ldadd = addend.data_ptr(), N
     L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc")
     return Cout
 
 
-def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, reduce=True):
+def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, reduce=True, defer=False, heads=None):
     """mode 2: dW[o, seg*N+i] = sum_{b,t} dZ[b,t,o] * X[b,t+shift[seg],i] -> fp32 [M, nseg*N], straight from the row-major
     activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
-    split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic)."""
+    split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic).
+
+    `defer` (backward passes): the fixed-order sum -- and, for problems too small for the CTA-pair kernel, the GEMM
+    itself -- is recorded and runs in the batched launches at the end of the backward pass (see flush_deferred).
+    `heads` = (grads, P, H, D, dk): the result is the packed gradient [(p,h,j), d] of P per-head projection tensors and
+    is summed straight into the reference's per-head layout g_p[h, d, j] (T/SubLayers.py:29-31)."""
     assert dZ.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dZ.is_contiguous() and X.is_contiguous()
-    if M % 256 == 0 and N % 256 == 0:          # CTA-pair kernel: 256x256 tiles on two SMs, reduction split in 128-frame units
+    pair = M % 256 == 0 and N % 256 == 0
+    if pair:          # CTA-pair kernel: 256x256 tiles on two SMs, reduction split in 128-frame units
         tiles = 2 * (M // 256) * (N // 256) * nseg
         units = Bt * ((T + 127) // 128)
         splits = max(1, min(units, 148 // max(1, tiles)))
@@ -710,6 +985,11 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, re
     else:
         tiles = ((M + 127) // 128) * ((N + 127) // 128) * nseg
         splits = max(1, min(Bt, 148 // max(1, tiles)))
+        if defer and DEFER_ENABLED:
+            # grouped launch: the problem does not have to fill the GPU on its own, so a CTA should get at least ~8
+            # reduction steps of 64 frames (a split that reduces one 63-token utterance is all prologue and epilogue)
+            splits = max(1, min(splits, (Bt * ((T + 63) // 64)) // 8))
+        splits = -(-Bt // -(-Bt // splits))                # no empty splits (utterances per split rounds up)
     ws = torch.empty(splits, M, nseg * N, device=dZ.device, dtype=torch.float32)
     d = L.TcDesc()
     d.A, d.B, d.C, d.Ct, d.bias = dZ.data_ptr(), X.data_ptr(), ws.data_ptr(), 0, 0
@@ -719,13 +999,35 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, re
         d.shift[i] = int(sft)
     d.relu, d.c_dtype, d.splits = 0, L.PKA_F32, splits
     d.drop = L.NO_DROPOUT
-    L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
+    deferred = defer and _defer_schedule()
+    if deferred and not pair:
+        with _DEFER.lock:
+            _DEFER.wgrads.append(d)
+            _DEFER.keep.append((dZ, X, ws))
+    else:
+        L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
+    per = M * nseg * N
+    if heads is not None:
+        grads, P, H, D, dk = heads
+        assert M == P * H * dk and N == D and nseg == 1
+        if deferred:
+            for p_, g in enumerate(grads):
+                if g is not None:
+                    defer_reduce(ws, g, H * D * dk, splits, per, src_off=p_ * H * dk * D, kind=L.REDUCE_HEADS, D=D, dk=dk)
+        else:
+            gp = [L.ptr(g) for g in grads] + [C.c_void_p(0)] * (3 - P)
+            L.check(L.lib().pka_tc_reduce_heads(L.ptr(ws), gp[0], gp[1], gp[2], splits, P, H, D, dk, L.stream_ptr()),
+                    "tc_reduce_heads")
+        return grads
     if not reduce:
         return ws, splits                         # the caller sums the split partials itself (fused with its relayout)
     acc = (out is not None) if accumulate is None else bool(accumulate)
     if out is None:
         out = torch.empty(M, nseg * N, device=dZ.device, dtype=torch.float32)
-    L.check(L.lib().pka_tc_reduce(L.ptr(ws), L.ptr(out), C.c_int64(M * nseg * N), splits, int(acc), L.stream_ptr()), "tc_reduce")
+    if deferred:
+        defer_reduce(ws, out, per, splits, per, accumulate=acc)
+    else:
+        L.check(L.lib().pka_tc_reduce(L.ptr(ws), L.ptr(out), C.c_int64(per), splits, int(acc), L.stream_ptr()), "tc_reduce")
     return out
 
 
@@ -739,8 +1041,9 @@ def gate_to_bf16(x, Bt, T, N, y=None, scale=1.0):
     return out
 
 
-def gate_colsum(dy, y, scale, bias_like, Bt, T, N):
-    """dz = (y > 0 ? dy*scale : 0) as bf16 [Bt,T,N] (y None: plain bf16 copy) AND the bias gradient sum_rows(dz), one pass."""
+def gate_colsum(dy, y, scale, bias_like, Bt, T, N, defer=False):
+    """dz = (y > 0 ? dy*scale : 0) as bf16 [Bt,T,N] (y None: plain bf16 copy) AND the bias gradient sum_rows(dz), one pass.
+    `defer`: the fixed-order sum of the partial rows runs in the batched launch at the end of the backward pass."""
     L.require_cuda(dy, y)
     dy = dy.contiguous()
     rows = Bt * T
@@ -748,8 +1051,12 @@ def gate_colsum(dy, y, scale, bias_like, Bt, T, N):
     db = grad_buffer(bias_like)
     chunks = L.lib().pka_colsum_chunks(C.c_int64(rows))
     ws = torch.empty(chunks * N, device=dy.device, dtype=torch.float32)
-    L.check(L.lib().pka_gate_colsum(L.ptr(dy), L.dtype_code(dy), L.ptr(y), L.ptr(dz), L.ptr(db), L.ptr(ws), C.c_int64(rows), N,
-                                    C.c_float(scale), int(y is not None), L.stream_ptr()), "gate_colsum")
+    deferred = defer and _defer_schedule()
+    L.check(L.lib().pka_gate_colsum(L.ptr(dy), L.dtype_code(dy), L.ptr(y), L.ptr(dz), C.c_void_p(0) if deferred else L.ptr(db),
+                                    L.ptr(ws), C.c_int64(rows), N, C.c_float(scale), int(y is not None), L.stream_ptr()),
+            "gate_colsum")
+    if deferred:
+        defer_reduce(ws, db, N, L.lib().pka_gate_colsum_parts(L.dtype_code(dy), C.c_int64(rows), N), N)
     return dz, db
 
 
@@ -766,7 +1073,7 @@ class _LinearTcFn(torch.autograd.Function):
     weight-gradient).  Weights stay fp32 masters; their bf16 operand copies are made here, once per call."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, splice, relu, drop, out_fp32):
+    def forward(ctx, x, weight, bias, splice, relu, drop, out_fp32, link=None):
         L.require_cuda(x, weight, bias)
         assert x.dtype == torch.bfloat16 and x.dim() == 3 and x.is_contiguous()
         Bt, T, kin = x.shape
@@ -775,7 +1082,13 @@ class _LinearTcFn(torch.autograd.Function):
         N = w2.shape[0]
         assert w2.shape[1] == n_ctx * kin
         needs_dx = ctx.needs_input_grad[0]
-        wf, wd = weight_relayout(w2.detach(), kin, n_ctx, True, needs_dx)
+        if OPERANDS is not None and weight.is_contiguous():
+            wf, wd = OPERANDS.plain(weight, N, kin, n_ctx)         # refreshed once per forward pass, not per op
+        else:
+            wf, wd = weight_relayout(w2.detach(), kin, n_ctx, True, needs_dx)
+        if link is not None:
+            link.armed = bool(needs_dx) and not splice
+        ctx.link = link if (link is not None and link.armed) else None
         y = gemm_tc_rows(x, wf, Bt, T, N, kin, nseg=n_ctx, lda=kin, ldb=n_ctx * kin, b_seg_col=kin, shift=splice or (),
                          bias=bias, relu=relu, drop=drop, out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
         if relu and GATE_TAP is not None:
@@ -796,7 +1109,7 @@ class _LinearTcFn(torch.autograd.Function):
             assert y.dtype == torch.bfloat16
             scale = (1.0 / (1.0 - drop.p)) if use_drop else 1.0
             if want_db and N % 4 == 0:            # ReLU/dropout gate and bias gradient in one pass over dY
-                dz, db = gate_colsum(dy, y, scale, bias, Bt, T, N)
+                dz, db = gate_colsum(dy, y, scale, bias, Bt, T, N, defer=True)
                 want_db = False
             else:
                 dz = gate_to_bf16(dy, Bt, T, N, y=y, scale=scale)
@@ -809,26 +1122,32 @@ class _LinearTcFn(torch.autograd.Function):
             if dy.dtype == torch.bfloat16:
                 dz = dy
             elif want_db and N % 4 == 0:          # fp32 -> bf16 copy and bias gradient in one pass
-                dz, db = gate_colsum(dy, None, 1.0, bias, Bt, T, N)
+                dz, db = gate_colsum(dy, None, 1.0, bias, Bt, T, N, defer=True)
                 want_db = False
             else:
                 dz = gate_to_bf16(dy, Bt, T, N)
+        addend = ctx.link.take() if ctx.link is not None else None       # residual-branch gradient of the sub-layer input
         if ctx.needs_input_grad[0]:
             dx = gemm_tc_rows(dz, wd, Bt, T, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * N, b_seg_col=N,
-                              shift=[-c for c in splice])
+                              shift=[-c for c in splice], addend=addend)
         if ctx.needs_input_grad[1]:
             dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
-                               accumulate=False).view(wshape)
+                               accumulate=False, defer=True).view(wshape)
         if want_db:
-            db = colsum(dz.view(Bt * T, N), out=grad_buffer(bias), accumulate=False)
-        return dx, dw, db, None, None, None, None
+            hint = _COLSUM_HINTS.pop(dz.data_ptr(), None) if dz is dy else None
+            if hint is not None and hint[2] == Bt * T and hint[3] == N and _defer_schedule():
+                db = grad_buffer(bias)            # column sums of dz were left behind by the LayerNorm backward above us
+                defer_reduce(hint[0], db, N, hint[1], 3 * N, src_off=2 * N)
+            else:
+                db = colsum(dz.view(Bt * T, N), out=grad_buffer(bias), accumulate=False, defer=True)
+        return dx, dw, db, None, None, None, None, None
 
 
 GATE_TAP = None          # parity tests set this to a list: every [ReLU] tensor-core layer appends its output (call order)
 
 
-def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32=False):
-    return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32)
+def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32=False, link: Optional[ResidualLink] = None):
+    return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32, link)
 
 
 def transpose_to_bf16(weight_kn):

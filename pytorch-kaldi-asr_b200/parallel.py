@@ -111,6 +111,9 @@ class GradAllReduce:
         lo, hi = self.bounds[b]
         view = self.opt.flat_grad[lo:hi]
         self.launched[b] = True
+        if self.opt.flat_grad.is_cuda:
+            from . import ops
+            ops.flush_deferred()                  # the bucket's gradients may still be split partials: sum them first
         if self.world == 1:
             return
         if self.comm_stream is not None:
@@ -138,6 +141,9 @@ class GradAllReduce:
         """Send whatever has not gone out yet (no-overlap mode: everything), then join communication and compute."""
         if not self.enabled:
             return
+        if self.opt.flat_grad.is_cuda:
+            from . import ops
+            ops.flush_deferred()
         if self.symm_op is not None:
             self.symm_op(self.opt.flat_grad, "sum", self.group_name)
             return

@@ -240,16 +240,14 @@ def train_epoch(model, batch_loader, crit, mode='train', optimizer=None, batch_e
             else:
                 totals += out.double()
             continue
-        goal = tgt_seq[:, 1:]
-        tgt_in = tgt_seq[:, :-1]
-        tgt_in_mask = tgt_pad_mask[:, :-1]
+        tgt_in, goal, tgt_in_mask = ops.split_targets(tgt_seq, tgt_pad_mask)     # L/train.py:163-165, one launch
         if mode == 'train':
             optimizer.zero_grad()
             pred = model(src_seq, src_pad_mask, tgt_in, tgt_in_mask)
         else:
             with torch.no_grad():
                 pred = model(src_seq, src_pad_mask, tgt_in, tgt_in_mask)
-        loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), smoothing)
+        loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.view(-1), smoothing)
         if mode == 'train':
             loss.backward()
             if grad_sync is not None:
@@ -291,6 +289,7 @@ class GraphedTrainStep:
         self.model, self.optimizer, self.smoothing, self.grad_sync = model, optimizer, smoothing, grad_sync
         self.device = next(model.parameters()).device
         self.out = torch.zeros(3, device=self.device, dtype=torch.float32)
+        self._one = torch.ones((), device=self.device, dtype=torch.float32)
         self.warmup = warmup
         self.shapes = {}                                  # (B, T, F, L+1) -> dict(src, smask, tgt, tmask, graph)
         self.pool = None
@@ -372,18 +371,16 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     def _body(self, ent):
-        tgt = ent["tgt"]
-        goal = tgt[:, 1:]
+        tgt_in, goal, tmask_in = ops.split_targets(ent["tgt"], ent["tmask"])
         self.optimizer.zero_grad()
-        pred = self.model(ent["src"], ent["smask"], tgt[:, :-1], ent["tmask"][:, :-1])
-        loss, stats = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.contiguous().view(-1), self.smoothing)
-        loss.backward()
+        pred = self.model(ent["src"], ent["smask"], tgt_in, tmask_in)
+        # the loss kernel writes {loss, n_correct, n_words} straight into the step's result buffer
+        loss, _ = ops.cross_entropy_sum(pred.view(-1, pred.size(-1)), goal.view(-1), self.smoothing, out3=self.out)
+        loss.backward(self._one)                  # preallocated d(loss) = 1: no fill kernel per step
         if self.grad_sync is not None:
             self.grad_sync()
         self.optimizer.step()
         self.optimizer.update_learning_rate()
-        self.out[0].copy_(loss.detach())
-        self.out[1:].copy_(stats)
 
     def load(self, src, smask, tgt, tmask):
         ent = self.shapes.get(self._key(src, tgt))

@@ -195,6 +195,7 @@ class Transformer(nn.Module):
         self.encoder_type = encoder_type
         self.cmvn = cmvn
         self.dropout_state = _rng.DropoutState(seed)
+        self._operands = ops.OperandCache()      # bf16 GEMM operand copies of the weights, one refresh launch per forward
         if encoder_type == "tdnn":
             self.encoder_test = EncoderTest(lda_mat=lda_mat, n_src_dim=n_src_dim * src_fold,
                                             encoder_max_len=encoder_max_len, d_model=en_d_model, dropout=en_dropout,
@@ -225,6 +226,16 @@ class Transformer(nn.Module):
         return self.encoder(seq, mask)[0], mask
 
     def forward(self, src_seq, src_pad_mask, tgt_seq, tgt_pad_mask):
+        ops.reset_deferred()
+        if ops.compute_mode() == "bf16" and tgt_seq.size(1) > 1:
+            # tensor-core path: ONE launch refreshes every bf16 operand copy of the weights (they only change in the
+            # optimiser step) and advances the dropout step counter; the ops below find their operands in the cache
+            counter = self.dropout_state.step_tensor(src_seq.device) if self.training else None
+            self._operands.refresh(counter)
+            with self._operands.active():
+                enc_output, mask = self.encode(src_seq, src_pad_mask)
+                dec_output, *_ = self.decoder(tgt_seq, tgt_pad_mask, mask, enc_output)
+            return dec_output
         if self.training:
             self.dropout_state.tick(src_seq.device)
         enc_output, mask = self.encode(src_seq, src_pad_mask)

@@ -39,13 +39,14 @@ class LayerNormalization(nn.Module):
         self.a_2 = nn.Parameter(torch.ones(d_hid), requires_grad=True)
         self.b_2 = nn.Parameter(torch.zeros(d_hid), requires_grad=True)
 
-    def forward(self, z, residual=None, drop=None):
-        """LN(dropout(z) + residual); both extras default to the plain reference call LN(z).  Length-1 inputs (where
-        the reference skips normalisation) are handled by the callers, which fold the residual into their GEMM."""
+    def forward(self, z, residual=None, drop=None, link=None):
+        """LN(dropout(z) + residual); the extras default to the plain reference call LN(z).  Length-1 inputs (where
+        the reference skips normalisation) are handled by the callers, which fold the residual into their GEMM.
+        `link` (ops.ResidualLink): the residual branch of the gradient is handed to the sub-layer's first GEMM."""
         if z.size(1) == 1:
             assert residual is None and drop is None, "length-1 residual path is fused into the producing GEMM"
             return z
-        return ops.add_layer_norm(z, residual, self.a_2, self.b_2, self.eps, drop)
+        return ops.add_layer_norm(z, residual, self.a_2, self.b_2, self.eps, drop, link)
 
 
 class AttnMask:

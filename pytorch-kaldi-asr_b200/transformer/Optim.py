@@ -237,6 +237,8 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         assert closure is None
+        from .. import ops as _ops
+        _ops.flush_deferred()                     # normally a no-op: the backward pass has flushed its own reductions
         self._adopt_grads()
         g = self.param_groups[0]
         b1, b2 = g["betas"]

@@ -38,16 +38,18 @@ class MultiHeadAttention(nn.Module):
         if attn_mask is None or attn_mask.key_pad_mask is None:
             kp = torch.ones(k.shape[0], k.shape[1], dtype=torch.uint8, device=k.device)
             attn_mask = AttnMask(kp, attn_mask.band if attn_mask is not None else None)
+        # bf16 path: the residual branch of q's gradient joins the q-projection's data-gradient GEMM (ops.ResidualLink)
+        link = ops.ResidualLink() if (q.dtype == torch.bfloat16 and q.requires_grad and torch.is_grad_enabled()) else None
         if q is k and k is v:
-            qbuf, kvbuf = ops.head_proj(q, self.w_qs, self.w_ks, self.w_vs), None
+            qbuf, kvbuf = ops.head_proj(q, self.w_qs, self.w_ks, self.w_vs, link=link), None
         else:
             assert k is v, "keys and values come from the same tensor on this path (T/Layers.py:33-35)"
-            qbuf, kvbuf = ops.head_proj(q, self.w_qs), ops.head_proj(k, self.w_ks, self.w_vs)
+            qbuf, kvbuf = ops.head_proj(q, self.w_qs, link=link), ops.head_proj(k, self.w_ks, self.w_vs)
         ctx, probs = self.attention(qbuf, kvbuf, attn_mask, self.n_head, self.d_k, want_probs=self.return_attn)
         drop = self._rng.make(self.p, self._site, q.device, self.training)
         if q.dtype == torch.bfloat16:  # bf16 activation stream: tensor-core projections / attention, bf16 LayerNorm I/O
             assert q.size(1) > 1, "the bf16 path is the training path; single-token decoding runs in fp32"
-            return self.layer_norm(self.proj(ctx), residual=q, drop=drop), probs
+            return self.layer_norm(self.proj(ctx), residual=q, drop=drop, link=link), probs
         if q.size(1) == 1:          # LayerNormalization is the identity for length-1 inputs (T/Modules.py:43-44)
             out = self.proj(ctx, drop=drop, residual=q)
         else:
@@ -73,9 +75,10 @@ class PositionwiseFeedForward(nn.Module):
     def forward(self, x):
         drop = self._rng.make(self.p, self._site, x.device, self.training)
         if x.dtype == torch.bfloat16:  # both GEMMs on tcgen05 with fused bias(+ReLU) epilogues
-            h = ops.linear_tc(x, self.w_1.weight, self.w_1.bias, relu=True)
+            link = ops.ResidualLink() if (x.requires_grad and torch.is_grad_enabled()) else None
+            h = ops.linear_tc(x, self.w_1.weight, self.w_1.bias, relu=True, link=link)
             y = ops.linear_tc(h, self.w_2.weight, self.w_2.bias)
-            return self.layer_norm(y, residual=x, drop=drop)
+            return self.layer_norm(y, residual=x, drop=drop, link=link)
         h = ops.linear(x, self.w_1.weight, self.w_1.bias, relu=True)
         if x.size(1) == 1:
             return ops.linear(h, self.w_2.weight, self.w_2.bias, drop=drop, residual=x)

@@ -62,7 +62,7 @@ def test_struct_layouts_match_the_header(library):
     src = r'''
     #include <stdio.h>
     #include "pka_b200.h"
-    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(pka_dropout), sizeof(pka_gemm_desc), sizeof(pka_attn_desc), sizeof(pka_beam_desc)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(pka_dropout), sizeof(pka_gemm_desc), sizeof(pka_attn_desc), sizeof(pka_beam_desc), sizeof(pka_tc_desc), sizeof(pka_reduce_job), sizeof(pka_relayout_job)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -72,7 +72,8 @@ def test_struct_layouts_match_the_header(library):
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(library.Dropout), ctypes.sizeof(library.GemmDesc), ctypes.sizeof(library.AttnDesc),
-                     ctypes.sizeof(library.BeamDesc)]
+                     ctypes.sizeof(library.BeamDesc), ctypes.sizeof(library.TcDesc), ctypes.sizeof(library.ReduceJob),
+                     ctypes.sizeof(library.RelayoutJob)]
 
 
 def test_product_package_never_imports_the_oracle():
