@@ -869,7 +869,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"])
-    ap.add_argument("--padding", default=os.environ.get("PKA_BENCH_PADDING", "set"), choices=["set", "bucket"])
+    ap.add_argument("--padding", default=os.environ.get("PKA_BENCH_PADDING", "bucket"), choices=["set", "bucket"],
+                    help="bucket: length-sorted batches padded to a few bucket lengths (one CUDA graph each); set: the "
+                         "reference loader's whole-set padding")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")

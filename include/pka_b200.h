@@ -281,6 +281,12 @@ int pka_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr_host, int64_t* state, float beta1, float beta2, float eps, void* bf16_shadow,
                   void* stream);
 int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream);
+/* pka_adam_step + the counter updates in ONE launch: the last CTA to finish stores adam_t+1 and, if tick_lr, performs
+ * pka_lr_tick's update (every CTA has read adam_t / lr before any CTA can be last).  done_counter: uint32[1], zero
+ * before the first call (it resets itself). */
+int pka_adam_step_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* lr_dev,
+                        float lr_host, int64_t* state, float beta1, float beta2, float eps, void* bf16_shadow,
+                        uint32_t* done_counter, int tick_lr, float start_lr, float soft_coefficient, void* stream);
 
 /* ---- host side of the input feed (no device work) --------------------------------------------------------------------
  * replaces: pad_to_longest over the features of a batch (U/instances_handler.py:118-139, U/BatchLoader.py:92-103).

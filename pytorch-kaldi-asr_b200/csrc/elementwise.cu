@@ -389,9 +389,10 @@ __global__ void transpose_kernel(const S* __restrict__ s, Dt* __restrict__ d, in
 // ---------------------------------------------------------------------------------------------- optimiser
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-            float* __restrict__ v, long long n, const float* __restrict__ lr_dev, float lr_host,
-            const long long* __restrict__ state, float b1, float b2, float eps,
-            __nv_bfloat16* __restrict__ shadow) {
+            float* __restrict__ v, long long n, const float* lr_dev, float lr_host,
+            const long long* state, float b1, float b2, float eps,
+            __nv_bfloat16* __restrict__ shadow, unsigned int* done, long long* state_w,
+            float* lr_w, int tick_lr, float tick_start_lr, float tick_c) {
   pdl_wait();
   __shared__ float s_step, s_isb2;
   if (threadIdx.x == 0) {
@@ -424,6 +425,25 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     upd(g[e], mv, vv, pv);
     m[e] = mv; v[e] = vv; p[e] = pv;
     if (shadow) shadow[e] = __float2bfloat16_rn(pv);
+  }
+  // The counters advance inside this launch: every CTA read adam_t / lr at its start, so the LAST CTA to finish may
+  // store adam_t + 1 (and, when asked, tick the LR schedule: n += 1; lr = start_lr*c/(n+c), T/Optim.py:21-27) without a
+  // race -- two single-thread kernels less per step.  `done` is a zero-initialised counter that resets itself.
+  if (done) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(done, 1u);
+      if (prev == gridDim.x - 1) {
+        state_w[0] += 1;
+        if (tick_lr) {
+          state_w[1] += 1;
+          lr_w[0] = (tick_start_lr * tick_c) / ((float)state_w[1] + tick_c);
+        }
+        *done = 0u;
+        __threadfence();
+      }
+    }
   }
 }
 __global__ void adam_t_inc_kernel(long long* state) {
@@ -599,11 +619,28 @@ extern "C" int pka_adam_step(float* param, const float* grad, float* exp_avg, fl
   PKA_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && n > 0, PKA_EINVAL, "adam_step: bad arguments");
   cudaStream_t st = as_stream(stream);
   PKA_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), PKA_EALIGN, "adam_step: the arenas must be 16-byte aligned");
-  launch_k(adam_kernel, grid_for((n + 3) / 4, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow);
+  launch_k(adam_kernel, grid_for((n + 3) / 4, 256), 256, 0, st, param, grad, exp_avg, exp_avg_sq, n, lr_dev, lr_host, (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow,
+           (unsigned int*)nullptr, (long long*)nullptr, (float*)nullptr, 0, 0.f, 0.f);
   int rc = check_launch("adam");
   if (rc) return rc;
   launch_k(adam_t_inc_kernel, 1, 1, 0, st, (long long*)state);
   return check_launch("adam_t_inc");
+}
+
+// pka_adam_step with the counter updates folded into the same launch (see adam_kernel): adam_t += 1 always; when
+// tick_lr != 0 also the LR schedule tick of pka_lr_tick (lr_dev must then be given).  done_counter: uint32[1], zero
+// before the first call, owned by the caller.
+extern "C" int pka_adam_step_fused(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   float* lr_dev, float lr_host, int64_t* state, float beta1, float beta2, float eps,
+                                   void* bf16_shadow, uint32_t* done_counter, int tick_lr, float start_lr,
+                                   float soft_coefficient, void* stream) {
+  PKA_REQUIRE(param && grad && exp_avg && exp_avg_sq && state && done_counter && n > 0 && (!tick_lr || lr_dev), PKA_EINVAL,
+              "adam_step_fused: bad arguments");
+  PKA_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), PKA_EALIGN, "adam_step_fused: the arenas must be 16-byte aligned");
+  launch_k(adam_kernel, grid_for((n + 3) / 4, 256), 256, 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, (const float*)lr_dev, lr_host,
+           (const long long*)state, beta1, beta2, eps, (__nv_bfloat16*)bf16_shadow, (unsigned int*)done_counter, (long long*)state, lr_dev,
+           tick_lr, start_lr, soft_coefficient);
+  return check_launch("adam_fused");
 }
 
 extern "C" int pka_lr_tick(float* lr_dev, int64_t* state, float start_lr, float soft_coefficient, void* stream) {

@@ -203,12 +203,16 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 if (nbx == 2) tma_load_3d(dst + box_bytes, &mapB, full, col + R2_BK, row, 0);
               }
             }
-            if (a_next < p.kb_per_seg) issue_a();
-            if (a_next < p.kb_per_seg) issue_a();
+            // producer 0 owns the activations but only every other weight stage: after its turn at stage i the K
+            // blocks of stages i+1 and i+2 must be on their way (four blocks per turn; two were not enough when a
+            // problem has fewer weight stages than K-block pairs, e.g. K = 512 -> N = 128: blocks 6 and 7 never came)
+#pragma unroll 1
+            for (int r = 0; r < 4 && a_next < p.kb_per_seg; ++r) issue_a();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
       }
+      while (a_next < p.kb_per_seg) issue_a();     // (pid 1 starts at kb_per_seg: no-op there)
       if (pid == 0) stamp(p.dbg, 4);
     }
   } else if (warp == 1) {
@@ -455,8 +459,11 @@ static bool plan_rows2(const pka_tc_desc* d, Rows2Plan* pl) {
       for (int ci = 0; ci < 3 && !pair; ++ci) {
         const int c = cand[ci];
         if (c <= 0 || d->N % c != 0) continue;
-        const int per_cta = d->N < 512 ? d->N : 512;
-        if (per_cta % c != 0 || d->N % per_cta != 0) continue;
+        // columns per CTA: the largest multiple of the chunk that divides N and fits the 512 TMEM columns
+        // (N = 768, the fused cross-attention k|v projection of three layers: 256 per CTA, three grid rows)
+        int per_cta = (d->N < 512 ? d->N : 512) / c * c;
+        while (per_cta >= c && d->N % per_cta != 0) per_cta -= c;
+        if (per_cta < c) continue;
         if (budget0 / (c * 128) < need) continue;
         pair = 1; chunk = c; nt = per_cta / c; pair_gy = d->N / per_cta;
       }

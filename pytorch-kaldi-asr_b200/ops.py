@@ -198,6 +198,7 @@ def reset_deferred():
     with d.lock:
         d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
     _COLSUM_HINTS.clear()
+    _PACKS.clear()
 
 
 # LayerNorm backward also leaves the column sums of the gradient it hands to the layer below (its dx) as partial rows in
@@ -506,19 +507,24 @@ class _AttnTcFn(torch.autograd.Function):
     Same packed-buffer convention as _AttnFn; q/k/v and the output are bf16, statistics fp32."""
 
     @staticmethod
-    def forward(ctx, qbuf, kvbuf, key_mask, H, dk, band, scale, drop, out_fp32):
+    def forward(ctx, qbuf, kvbuf, key_mask, H, dk, band, scale, drop, out_fp32, kv_pack=None):
         L.require_cuda(qbuf, kvbuf, key_mask)
         ctx.set_materialize_grads(False)          # no zero-filled gradient for the lse output
         assert qbuf.dtype == torch.bfloat16 and (kvbuf is None or kvbuf.dtype == torch.bfloat16)
         qbuf = qbuf.contiguous()
         HD = H * dk
         B, Lq = qbuf.shape[0], qbuf.shape[1]
+        ctx.kv_pack = None
         if kvbuf is None:
             Lk, ldq = Lq, 3 * HD
             q_p, k_p, v_p, ldk = qbuf.data_ptr(), qbuf.data_ptr() + 2 * HD, qbuf.data_ptr() + 4 * HD, 3 * HD
         else:
-            kvbuf = kvbuf.contiguous()
-            Lk, ldq, ldk = kvbuf.shape[1], HD, 2 * HD
+            # k|v may be a column block of a wider packed buffer (cross-attention K/V of all layers from one GEMM)
+            if not (kvbuf.stride(2) == 1 and kvbuf.stride(0) == kvbuf.shape[1] * kvbuf.stride(1) and kvbuf.stride(1) % 8 == 0):
+                kvbuf = kvbuf.contiguous()
+            elif kv_pack is not None:
+                ctx.kv_pack = kv_pack
+            Lk, ldq, ldk = kvbuf.shape[1], HD, kvbuf.stride(1)
             q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 2 * HD
         key_mask = key_mask.to(torch.uint8).contiguous()
         assert key_mask.shape == (B, Lk)
@@ -541,7 +547,7 @@ class _AttnTcFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, _dlse):
         if dout is None:
-            return (None,) * 9
+            return (None,) * 10
         qbuf, kvbuf, key_mask, out, lse = ctx.saved_tensors
         d = ctx.desc
         HD = d.H * d.dk
@@ -553,7 +559,12 @@ class _AttnTcFn(torch.autograd.Function):
             q_p, k_p, v_p = qbuf.data_ptr(), qbuf.data_ptr() + 2 * HD, qbuf.data_ptr() + 4 * HD
             dq_p, dk_p, dv_p = dqbuf.data_ptr(), dqbuf.data_ptr() + 2 * HD, dqbuf.data_ptr() + 4 * HD
         else:
-            dkvbuf = torch.empty_like(kvbuf)
+            if ctx.kv_pack is not None:            # gradient goes straight into its column block of the shared packed buffer
+                dkvbuf = ctx.kv_pack.slot_like(kvbuf)
+            elif kvbuf.is_contiguous():
+                dkvbuf = torch.empty_like(kvbuf)
+            else:
+                dkvbuf = torch.empty_strided(kvbuf.shape, kvbuf.stride(), device=kvbuf.device, dtype=kvbuf.dtype)
             q_p, k_p, v_p = qbuf.data_ptr(), kvbuf.data_ptr(), kvbuf.data_ptr() + 2 * HD
             dq_p, dk_p, dv_p = dqbuf.data_ptr(), dkvbuf.data_ptr(), dkvbuf.data_ptr() + 2 * HD
         delta = torch.empty_like(lse)
@@ -565,7 +576,7 @@ class _AttnTcFn(torch.autograd.Function):
             L.check(L.lib().pka_attn_bwd(C.byref(d), L.PKA_BF16, C.c_void_p(q_p), C.c_void_p(k_p), C.c_void_p(v_p),
                                          L.ptr(key_mask), L.ptr(out), L.ptr(dout), L.ptr(lse), L.ptr(delta),
                                          C.c_void_p(dq_p), C.c_void_p(dk_p), C.c_void_p(dv_p), L.stream_ptr()), "attn_bwd")
-        return dqbuf, dkvbuf, None, None, None, None, None, None, None
+        return dqbuf, dkvbuf, None, None, None, None, None, None, None, None
 
 
 ATTN_BWD_TC = True      # False: the SIMT flash backward on the same bf16 buffers (kept for A/B comparison in the tests)
@@ -580,7 +591,84 @@ def attention(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, 
 def attention_tc(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: float, drop: Optional[Drop] = None,
                  out_fp32: bool = False):
     """bf16 packed projections -> bf16 (or fp32) context on the tcgen05 attention kernel; returns (out, lse)."""
-    return _AttnTcFn.apply(qbuf, kvbuf, key_mask, n_head, d_k, band, scale, drop, out_fp32)
+    return _AttnTcFn.apply(qbuf, kvbuf, key_mask, n_head, d_k, band, scale, drop, out_fp32,
+                           _PACKS.get(kvbuf.data_ptr()) if kvbuf is not None else None)
+
+
+_PACKS = {}           # address of a column-block view -> GradPack of its base (cleared at every forward pass)
+
+
+class GradPack:
+    """Gradient side of a packed multi-consumer buffer: every consumer writes its gradient into its own column block of
+    ONE buffer shaped like the forward buffer, so the producer's backward sees a single packed gradient."""
+
+    def __init__(self, base: torch.Tensor):
+        self.base_ptr, self.shape, self.stride, self.buf = base.data_ptr(), tuple(base.shape), base.stride(), None
+        self.item, self.device, self.dtype = base.element_size(), base.device, base.dtype
+
+    def slot_like(self, view: torch.Tensor) -> torch.Tensor:
+        if self.buf is None:
+            self.buf = torch.empty(self.shape, device=self.device, dtype=self.dtype)
+        off = (view.data_ptr() - self.base_ptr) // self.item           # element offset of the view inside the base
+        return self.buf.as_strided(view.shape, view.stride(), off)
+
+
+class _CrossKVFn(torch.autograd.Function):
+    """k|v projections of the encoder memory for ALL decoder layers in one tensor-core GEMM (the reference projects them
+    per layer, T/SubLayers.py:49-56 inside each DecoderLayer's enc_attn): out[..., (l*2 + p)*H*dk + h*dk + j] with p = 0
+    for w_ks, 1 for w_vs.  Returns one column-block view per layer; their gradients come back as column blocks of one
+    packed buffer (GradPack), so backward is ONE data-gradient GEMM (K = n_layers*2*H*dk) and ONE weight-gradient."""
+
+    @staticmethod
+    def forward(ctx, enc, *ws):
+        L.require_cuda(enc, *ws)
+        assert enc.dtype == torch.bfloat16 and enc.dim() == 3 and enc.is_contiguous() and len(ws) % 2 == 0
+        Bt, T, D = enc.shape
+        H, _, dk = ws[0].shape
+        P = len(ws)
+        ntot = P * H * dk
+        if OPERANDS is not None and all(w.is_contiguous() for w in ws):
+            wf, wd = OPERANDS.heads(ws)
+        else:
+            cache = OperandCache()
+            wf, wd = cache.heads(ws)
+        out = gemm_tc_rows(enc, wf, Bt, T, ntot, D, lda=D, ldb=D, out_dtype=torch.bfloat16)
+        ctx.save_for_backward(enc, wd, *ws)
+        ctx.meta = (Bt, T, D, H, dk, P)
+        ctx.pack = pack = GradPack(out)
+        views = tuple(out[:, :, l * 2 * H * dk:(l + 1) * 2 * H * dk] for l in range(P // 2))
+        for v in views[1:]:                        # (the first view shares the base address: registered last, below)
+            _PACKS[v.data_ptr()] = pack
+        _PACKS[views[0].data_ptr()] = pack
+        return views
+
+    @staticmethod
+    def backward(ctx, *ds):
+        enc, wd, *ws = ctx.saved_tensors
+        Bt, T, D, H, dk, P = ctx.meta
+        ntot, blk = P * H * dk, 2 * H * dk
+        pack = ctx.pack
+        ok = pack.buf is not None and all(
+            d is not None and d.data_ptr() == pack.buf.data_ptr() + 2 * l * blk and d.stride(1) == ntot for l, d in enumerate(ds))
+        if ok:
+            dz = pack.buf
+        else:                                      # a consumer bypassed the pack (or got no gradient): assemble it
+            dz = torch.cat([d if d is not None else torch.zeros(Bt, T, blk, device=enc.device, dtype=torch.bfloat16) for d in ds], dim=2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tc_rows(dz, wd, Bt, T, D, ntot, lda=ntot, ldb=ntot)
+        dws = [None] * P
+        if any(ctx.needs_input_grad[1:1 + P]):
+            dws = [grad_buffer(ws[p]) if ctx.needs_input_grad[1 + p] else None for p in range(P)]
+            # the packed weight gradient [(l,p,h,j), d] is summed per tensor into the reference layout [H, D, dk]
+            gemm_tc_wgrad(dz, enc, Bt, T, ntot, D, 1, (0,), defer=True, heads=(dws, P, H, D, dk))
+        return (dx, *dws)
+
+
+def cross_kv_proj(enc, layer_weights):
+    """[(w_ks, w_vs) per layer] -> list of bf16 k|v buffers [B, T, 2*H*dk], one per layer (column blocks of one GEMM output)."""
+    flat = [w for pair in layer_weights for w in pair]
+    return list(_CrossKVFn.apply(enc, *flat))
 
 
 # ------------------------------------------------------------------------------------------------ add + LayerNorm
@@ -1014,10 +1102,21 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, re
             for p_, g in enumerate(grads):
                 if g is not None:
                     defer_reduce(ws, g, H * D * dk, splits, per, src_off=p_ * H * dk * D, kind=L.REDUCE_HEADS, D=D, dk=dk)
-        else:
+        elif P <= 3:
             gp = [L.ptr(g) for g in grads] + [C.c_void_p(0)] * (3 - P)
             L.check(L.lib().pka_tc_reduce_heads(L.ptr(ws), gp[0], gp[1], gp[2], splits, P, H, D, dk, L.stream_ptr()),
                     "tc_reduce_heads")
+        else:                                      # more than three packed tensors: the job table, launched right away
+            jobs = []
+            for p_, g in enumerate(grads):
+                if g is not None:
+                    j = L.ReduceJob()
+                    j.src, j.dst = ws.data_ptr() + 4 * p_ * H * dk * D, g.data_ptr()
+                    j.n, j.split_stride, j.splits, j.kind, j.accumulate, j.D, j.dk = H * D * dk, per, splits, L.REDUCE_HEADS, 0, D, dk
+                    jobs.append(j)
+            if jobs:
+                arr = (L.ReduceJob * len(jobs))(*jobs)
+                L.check(L.lib().pka_reduce_jobs(arr, len(jobs), L.stream_ptr()), "reduce_jobs")
         return grads
     if not reduce:
         return ws, splits                         # the caller sums the split partials itself (fused with its relayout)

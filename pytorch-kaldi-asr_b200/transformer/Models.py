@@ -170,8 +170,13 @@ class Decoder(nn.Module):
         slf_mask = get_attn_padding_mask(tgt_pad_mask, tgt_pad_mask) + get_attn_subsequent_mask(tgt_pad_mask, *self.sub)
         enc_mask = get_attn_padding_mask(tgt_pad_mask, src_pad_mask)
         slf_attns, enc_attns = [], []
-        for layer in self.layer_stack:
+        # bf16 path: the cross-attention k|v projections of ALL layers are one GEMM over the encoder memory (the largest
+        # decoder GEMMs: every frame, every layer); layer l reads its column block
+        enc_kv = ops.cross_kv_proj(enc, [(l.enc_attn.w_ks, l.enc_attn.w_vs) for l in self.layer_stack]) \
+            if (bf16 and not return_attns) else None
+        for li, layer in enumerate(self.layer_stack):
             layer.slf_attn.return_attn = layer.enc_attn.return_attn = return_attns
+            layer.enc_attn.kv_override = enc_kv[li] if enc_kv is not None else None
             x, a1, a2 = layer(x, enc, slf_attn_mask=slf_mask, dec_enc_attn_mask=enc_mask)
             slf_attns.append(a1)
             enc_attns.append(a2)

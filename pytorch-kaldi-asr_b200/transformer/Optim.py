@@ -56,6 +56,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.dev_lr = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.use_device_lr = False                                            # switched on by ScheduledOptim
         self._peer = None                                                     # set by enable_peer_step()
+        self._done = torch.zeros(1, device=dev, dtype=torch.int32)            # CTA-completion counter of the fused step
 
     # ---- data parallel: gradient reduce-scatter + Adam + parameter all-gather in one kernel over peer memory ----
     def enable_peer_step(self, group=None, max_ctas: int = 32, multicast=None):
@@ -235,7 +236,9 @@ class FusedAdam(torch.optim.Optimizer):
         self.flat_grad.zero_()
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, lr_tick=None):
+        """`lr_tick` = (start_lr, soft_coefficient): also advance the device-side LR schedule in the same launch (what
+        ScheduledOptim.update_learning_rate would otherwise do with a kernel of its own); returns True if it did."""
         assert closure is None
         from .. import ops as _ops
         _ops.flush_deferred()                     # normally a no-op: the backward pass has flushed its own reductions
@@ -252,10 +255,14 @@ class FusedAdam(torch.optim.Optimizer):
                                              C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]), L.stream_ptr()),
                     "dp_adam_step")
             return
-        L.check(L.lib().pka_adam_step(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg),
-                                      L.ptr(self.exp_avg_sq), C.c_int64(self.numel), lr_dev, C.c_float(g["lr"]),
-                                      L.ptr(self.dev_state), C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]),
-                                      L.ptr(self.flat_shadow), L.stream_ptr()), "adam_step")
+        tick = lr_tick is not None and self.use_device_lr
+        L.check(L.lib().pka_adam_step_fused(L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg),
+                                            L.ptr(self.exp_avg_sq), C.c_int64(self.numel), lr_dev, C.c_float(g["lr"]),
+                                            L.ptr(self.dev_state), C.c_float(b1), C.c_float(b2), C.c_float(g["eps"]),
+                                            L.ptr(self.flat_shadow), L.ptr(self._done), int(tick),
+                                            C.c_float(lr_tick[0] if tick else 0.0), C.c_float(lr_tick[1] if tick else 0.0),
+                                            L.stream_ptr()), "adam_step_fused")
+        return tick
 
 
 class ScheduledOptim(object):
@@ -273,17 +280,24 @@ class ScheduledOptim(object):
             optimizer.use_device_lr = True
 
     def step(self):
-        self.optimizer.step()
+        if self._fused:
+            # the device-side schedule tick rides in the Adam launch; update_learning_rate() then only does the host math
+            self._ticked = bool(self.optimizer.step(lr_tick=(self.start_lr, self.soft_coefficient)))
+        else:
+            self.optimizer.step()
 
     def zero_grad(self):
         self.optimizer.zero_grad()
 
     def update_learning_rate(self):
+        """LR rule of T/Optim.py:21-27.  With a FusedAdam the device-side copy is normally advanced by step() itself;
+        calling this without a preceding step() (or after a peer-mode step) still ticks the device."""
         self.n_current_steps += 1
         new_lr = (self.start_lr * self.soft_coefficient) / (self.n_current_steps + self.soft_coefficient)
         for group in self.optimizer.param_groups:
             group["lr"] = new_lr
-        if self._fused:
+        if self._fused and not getattr(self, "_ticked", False):
             o = self.optimizer
             L.check(L.lib().pka_lr_tick(L.ptr(o.dev_lr), L.ptr(o.dev_state), C.c_float(self.start_lr),
                                         C.c_float(self.soft_coefficient), L.stream_ptr()), "lr_tick")
+        self._ticked = False

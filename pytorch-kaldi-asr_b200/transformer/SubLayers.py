@@ -30,6 +30,7 @@ class MultiHeadAttention(nn.Module):
         self._rng = rng
         self._site = rng.site(site + ".proj")
         self.return_attn = False
+        self.kv_override = None      # set per call by Decoder.forward: this layer's k|v block of the fused projection
         init.xavier_normal_(self.w_qs)
         init.xavier_normal_(self.w_ks)
         init.xavier_normal_(self.w_vs)
@@ -44,7 +45,10 @@ class MultiHeadAttention(nn.Module):
             qbuf, kvbuf = ops.head_proj(q, self.w_qs, self.w_ks, self.w_vs, link=link), None
         else:
             assert k is v, "keys and values come from the same tensor on this path (T/Layers.py:33-35)"
-            qbuf, kvbuf = ops.head_proj(q, self.w_qs, link=link), ops.head_proj(k, self.w_ks, self.w_vs)
+            kvbuf, self.kv_override = self.kv_override, None
+            if kvbuf is None:
+                kvbuf = ops.head_proj(k, self.w_ks, self.w_vs)
+            qbuf = ops.head_proj(q, self.w_qs, link=link)
         ctx, probs = self.attention(qbuf, kvbuf, attn_mask, self.n_head, self.d_k, want_probs=self.return_attn)
         drop = self._rng.make(self.p, self._site, q.device, self.training)
         if q.dtype == torch.bfloat16:  # bf16 activation stream: tensor-core projections / attention, bf16 LayerNorm I/O

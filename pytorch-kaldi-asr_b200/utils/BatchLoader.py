@@ -18,7 +18,9 @@ What is different underneath, because the consumer is a ~1.5 ms GPU step rather 
 * `pad_to='dataset'` (what the reference does when pre-loading: every batch has the shape of the longest utterance of
   the set, which is also what a CUDA-graph replay needs) or `'batch'` (what it does when streaming), independent of
   `pre_load`; `pad_multiple` rounds the frame axis up; `bucket=K` sorts by length inside windows of K batches so that
-  'batch' padding wastes little;
+  'batch' padding wastes little; `pad_to='bucket'` pads a batch to `synthetic.bucket_length` (longest + 16 frames of
+  context, rounded to 64, at most the set length) and its labels to a multiple of 8: a handful of shapes, one CUDA
+  graph each, with results on real frames equal to whole-set padding (tests/test_gpu_bucketed.py);
 * the feature gather of a pre-loaded batch runs in the native library (`pka_host_pack_batch`; `pack_threads` > 1
   splits the rows over host threads -- measured: the copy is memory-bound and one thread is fastest on the 8-core
   build container -- and 0 selects the numpy loop, which the tests hold the native path to bit for bit);
@@ -58,8 +60,8 @@ class BatchLoader:
             raise ValueError('[ERROR] mode of BatchLoader can only be [all] or [drop]')
         if batch_size < 1:
             raise ValueError('[ERROR] batch_size must be positive')
-        if pad_to not in (None, 'dataset', 'batch'):
-            raise ValueError("[ERROR] pad_to can only be 'dataset' or 'batch'")
+        if pad_to not in (None, 'dataset', 'batch', 'bucket'):
+            raise ValueError("[ERROR] pad_to can only be 'dataset', 'batch' or 'bucket'")
         rank, world = shard
         if not 0 <= rank < world:
             raise ValueError('[ERROR] shard must be (rank, world) with 0 <= rank < world')
@@ -98,7 +100,7 @@ class BatchLoader:
             self._preload()
             if self.print_info:
                 print('[INFO] data preloaded.')
-        elif self.pad_to == 'dataset' or self.bucket:
+        elif self.pad_to in ('dataset', 'bucket') or self.bucket:
             raise ValueError("[ERROR] pad_to='dataset' and length bucketing need utterance lengths: use pre_load=True")
         if self.print_info:
             print('[INFO] loader initialized. data size:{}, batch_size:{}, iter per epoch:{}.'
@@ -201,6 +203,13 @@ class BatchLoader:
             t_max = int(self._src_len.max()) if self.pad_to == 'dataset' else int(self._src_len[list(idx)].max())
         t_pad = self._round_up(t_max)
         l_pad = self._max_tgt if self.pad_to == 'dataset' else int(self._tgt_len[list(idx)].max())
+        if self.pad_to == 'bucket':
+            # a few padded shapes (one CUDA graph each, train.GraphedTrainStep) instead of one per batch: frames to the
+            # next multiple of 64 that leaves the TDNN stack's 16 frames of right context as padding (results on real
+            # frames then equal those under whole-set padding), never beyond the whole-set length; labels to 8 tokens
+            from .synthetic import bucket_length
+            t_pad = bucket_length(t_max, int(self._src_len.max()))
+            l_pad = min(self._max_tgt, (l_pad - 1 + 7) // 8 * 8 + 1)
         b = len(idx)
         src, src_mask, tgt, tgt_mask = alloc([((b, t_pad, dim), _DTYPES[0]), ((b, t_pad), _DTYPES[1]),
                                               ((b, l_pad), _DTYPES[2]), ((b, l_pad), _DTYPES[3])])

@@ -39,6 +39,9 @@ def rnd(*shape, seed=0, scale=1.0):
     (2, 300, 256, 128, None, False, False),      # enc_dec_projection
     (3, 333, 512, 512, None, True, True),        # config-5 FFN: 128 KB of resident activations, 128-column chunks
     (2, 200, 512, 1536, None, False, False),     # config-5 packed q|k|v projection: output columns over grid.y
+    (4, 300, 512, 128, None, False, True),       # 8 resident K blocks but only 4 weight stages (hung in round 2 before the
+                                                 # activation producer issued four blocks per turn)
+    (2, 200, 128, 768, None, False, False),      # fused cross-attention k|v of three layers: 256 columns per CTA, 3 grid rows
 ])
 def test_linear_tc_fwd_bwd(Bt, T, kin, N, ctx, relu, bias):
     from pytorch_kaldi_asr_b200 import ops
