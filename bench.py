@@ -560,6 +560,35 @@ def dp_parity_check(model, opt, sync, pool, rank, world, pk, mode):
         sync.finish()
     inner._adopt_grads()
     g_dp = inner.flat_grad.clone()
+    if sync is None:
+        # peer mode: the gradients are summed inside the fused optimiser kernel, never in place.  Sum a copy with NCCL
+        # for the comparison below, and hold the kernel itself to {NCCL SUM, local Adam} on the same state.
+        import ctypes as C
+        from pytorch_kaldi_asr_b200 import _lib as L
+        dist.all_reduce(g_dp, op=dist.ReduceOp.SUM)
+        inner.sync_moments()
+        state = [inner.flat_param, inner.exp_avg, inner.exp_avg_sq, inner.dev_state, inner.dev_lr, inner.flat_grad]
+        snap = [t.clone() for t in state]
+        inner.step()                                               # the peer kernel (collective)
+        torch.cuda.synchronize()
+        dist.barrier()
+        after_peer = inner.flat_param.clone()
+        for t, s_ in zip(state, snap):
+            t.copy_(s_)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g = inner.param_groups[0]
+        L.check(L.lib().pka_adam_step(L.ptr(inner.flat_param), L.ptr(g_dp), L.ptr(inner.exp_avg), L.ptr(inner.exp_avg_sq),
+                                      C.c_int64(inner.numel), L.ptr(inner.dev_lr), C.c_float(g["lr"]), L.ptr(inner.dev_state),
+                                      C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]), C.c_void_p(0),
+                                      L.stream_ptr()), "adam_step")
+        torch.cuda.synchronize()
+        out["peer_step_max_abs_diff_vs_nccl_sum_plus_adam"] = float((after_peer - inner.flat_param).abs().max())
+        out["peer_step_bit_identical"] = bool(torch.equal(after_peer, inner.flat_param))
+        for t, s_ in zip(state, snap):
+            t.copy_(s_)
+        torch.cuda.synchronize()
+        dist.barrier()
     loss_sum = loss.detach().clone().double()
     dist.all_reduce(loss_sum)
     gathered = [[torch.empty_like(t) for _ in range(world)] for t in dev]
@@ -603,7 +632,8 @@ def dp_parity_check(model, opt, sync, pool, rank, world, pk, mode):
     if rank == 0:
         out["ok"] = bool(out["params_bit_identical"] and out["sharded_decode_equals_unsharded"]
                          and out["grad_rel_err_vs_single_process"] <= out["grad_tolerance"]
-                         and out["loss_rel_err_vs_single_process"] <= 1e-5)
+                         and out["loss_rel_err_vs_single_process"] <= 1e-5
+                         and out.get("peer_step_max_abs_diff_vs_nccl_sum_plus_adam", 0.0) <= 1e-6)
     return out
 
 

@@ -7,10 +7,15 @@
 //   warp 4 lane 0   TMA producer: Q once, then K_j / V_j boxes [128 keys][64] (128B swizzle, OOB rows zero-filled)
 //   warp 5 lane 0   MMA issuer:   S = Q K_j^T   (tcgen05.mma 128x128x16 x4, both operands K-major)  -> TMEM cols [0,128)
 //                                 O_j = P_j V_j (tcgen05.mma 128x64x16  x8, P K-major from smem, V MN-major) -> TMEM cols [128,192)
-//   warps 0-3       online softmax, one thread per query row (TMEM lane = row): tcgen05.ld S, mask predicate
-//                   (key padding via warp ballot of the u8 mask, band via per-row bit range), running max / sum in the
-//                   exp2 domain, P_j written to shared memory as bf16 in the UMMA K-major 128B-swizzle layout, then
-//                   O += alpha-rescaled accumulation in registers from the TMEM partial product.
+//   warps 0-3       online softmax, one thread per query row (TMEM lane = row): ONE tcgen05.ld pass brings the 128 scores
+//                   of the tile into registers, mask predicate (key padding via warp ballot of the u8 mask, band via
+//                   per-row bit range; chunks of 32 keys that are all allowed skip the per-element tests), running
+//                   reference maximum / sum in the exp2 domain, P_j written to shared memory as bf16 in the UMMA K-major
+//                   128B-swizzle layout.
+//   O stays in TENSOR MEMORY for the whole key loop: P_j V_j accumulates into it (round 1 pulled every partial product
+//   into registers and rescaled 64 accumulators per tile).  The exponent reference m_ref is only raised -- and O / l
+//   rescaled through tcgen05.ld / tcgen05.st -- when a tile's maximum exceeds it by more than 2^8 (lazy rescale: the
+//   probabilities then stay below 256, far inside bf16 / fp32 range, and the result is mathematically the same).
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
 // The [B*H, Lq, Lk] probability tensor never exists; rows without an allowed key give 0 output and lse = -inf.
 #include "tc_common.cuh"
@@ -47,9 +52,9 @@ __device__ __forceinline__ float fast_exp2(float x) {       // MUFU.EX2 (2 ulp);
 constexpr uint32_t kIdescS = make_idesc(AT_BM, AT_BN);                  // S = Q K^T
 constexpr uint32_t kIdescO = make_idesc(AT_BM, AT_D, false, true);      // O = P V  (V is MN-major)
 
-// FAST (PKA_ATTN_FAST=1, default off until measured): chunks of 32 keys whose keys are all allowed (the common case away
-// from the band edge and the padded tail) skip the per-element mask tests, and the tile maximum is taken on the raw
-// scores and scaled once (x -> round(x * c) is monotone for c > 0, so the result is bit-identical).
+// Chunks of 32 keys whose keys are all allowed (the common case away from the band edge and the padded tail) skip the
+// per-element mask tests; the tile maximum is taken on the raw scores and scaled once (monotone for scale > 0).
+// FAST (PKA_ATTN_FAST=1): single pass over the scores (all 128 of a row in registers); default: two tensor-memory passes.
 template <bool FAST>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -127,11 +132,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk) {  // P: K-block (64 keys) = 16 KB, 32 B per step inside; V: 16 key rows = 2 KB
           const uint64_t da = dp + (uint64_t)((kk >> 2) * (AT_BM * 128 / 16) + (kk & 3) * 2);
-          umma_f16(tmem_O, da, dv + (uint64_t)(kk * 128), kIdescO, kk ? 1u : 0u);
+          umma_f16(tmem_O, da, dv + (uint64_t)(kk * 128), kIdescO, (j | kk) ? 1u : 0u);   // O accumulates over all tiles
         }
-        umma_commit(smem_u32(&bars[7]));           // O_j partial product ready
         umma_commit(smem_u32(&bars[3 + s]));       // K_j / V_j stage free
       }
+      umma_commit(smem_u32(&bars[7]));             // O complete
     }
   } else {                                         // ===== softmax warps 0..3: thread = query row
     const int r = warp * 32 + lane;
@@ -141,15 +146,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const uint8_t* km = p.kmask + (long long)b * p.Lk;
     const DropCtx dc = make_drop(p.drop);
     const unsigned long long drop_row = (((unsigned long long)b * p.H + h) * p.Lq + (row_ok ? i : 0)) * (unsigned long long)((p.Lk + 7) & ~7);
-    float m_run = -CUDART_INF_F, l_run = 0.f;
-    float o[AT_D];
-#pragma unroll
-    for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+    float m_ref = -CUDART_INF_F, l_run = 0.f;      // exponent reference (>= every score seen minus 8), running sum
     uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+    constexpr float kLazy = 8.f;                   // raise the reference only when a tile exceeds it by 2^8
 
     // allowed-key bit masks (key padding by warp ballot, band as a per-row bit range) and dropout keep bits of this
     // row for the 4 chunks of 32 keys of a tile.  Both depend on indices only, so the masks of tile j+1 are built while
-    // the tensor core runs P_j V_j (the thread would otherwise just wait for that product).
+    // the tensor core runs P_j V_j (the thread would otherwise just wait for the next scores).
     uint32_t allow[4], keep[4];
     auto tile_masks = [&](int jt, uint32_t (&al)[4], uint32_t (&kp)[4]) {
       const int jb = (tile_lo + jt) * AT_BN;
@@ -175,51 +178,69 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     if (n_tiles > 0) tile_masks(0, allow, keep);
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(smem_u32(&bars[5]), j & 1);
+      mbar_wait(smem_u32(&bars[5]), j & 1);        // S_j complete -- and with it every earlier MMA (P_{j-1} V_{j-1} included)
       tc_fence_after();
-      // pass 1: tile maximum of the scaled scores (exp2 domain)
+      // FAST: the whole score row of the tile stays in registers (four loads in flight, one wait, one pass);
+      // otherwise the maximum is taken chunk by chunk and the scores are loaded again for the exponentials (fewer
+      // live registers, twice the tensor-memory reads)
+      uint32_t sv[4][32];
       float t_max = -CUDART_INF_F;
+      if (FAST) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tmem_S + lane_addr + (uint32_t)(c * 32), sv[c]);
+        tmem_ld_wait();
+      }
+      // tile maximum on the raw scores (scaled once: x -> x * c is monotone for c > 0)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv);
-        if (FAST) {                                // raw maximum; scaled once below
-          if (allow[c] == 0xffffffffu) {
+        if (!FAST) tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
+        const uint32_t (&x)[32] = FAST ? sv[c] : sv[0];
+        if (allow[c] == 0xffffffffu) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) t_max = fmaxf(t_max, __uint_as_float(sv[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(sv[e]));
-          }
-        } else {
+          for (int e = 0; e < 32; ++e) t_max = fmaxf(t_max, __uint_as_float(x[e]));
+        } else if (allow[c] != 0u) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(sv[e]) * p.scale_log2);
+            if ((allow[c] >> e) & 1u) t_max = fmaxf(t_max, __uint_as_float(x[e]));
         }
       }
-      if (FAST) t_max *= p.scale_log2;             // scale_log2 > 0: -inf stays -inf
-      const float m_new = fmaxf(m_run, t_max);
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = (m_run == -CUDART_INF_F) ? 0.f : fast_exp2(m_run - m_new);
-      // pass 2: probabilities -> bf16 P tile in shared memory (UMMA K-major, 128B swizzle)
+      t_max *= p.scale_log2;                       // scale_log2 > 0: -inf stays -inf
+      // lazy reference update: first allowed key of the row, or a tile that exceeds the reference by more than 2^kLazy
+      const bool first = (m_ref == -CUDART_INF_F) && (t_max != -CUDART_INF_F);
+      const bool raise = (m_ref != -CUDART_INF_F) && (t_max > m_ref + kLazy);
+      if (__any_sync(0xffffffffu, raise)) {        // rescale O (tensor memory) and l of the rows that moved; rare after tile 0
+        const float alpha = raise ? fast_exp2(m_ref - t_max) : 1.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+          tmem_st32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
+        }
+        tmem_st_wait();
+        l_run *= alpha;
+      }
+      if (first || raise) m_ref = t_max;
+      const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
+      // probabilities -> bf16 P tile in shared memory (UMMA K-major, 128B swizzle)
       float l_tile = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv);
         float pv[32];
-        if (FAST && allow[c] == 0xffffffffu) {
+        if (!FAST) tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
+        const uint32_t (&x)[32] = FAST ? sv[c] : sv[0];
+        if (allow[c] == 0xffffffffu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const float pe = fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use));
+            const float pe = fast_exp2(fmaf(__uint_as_float(x[e]), p.scale_log2, -m_use));
             l_tile += pe;
             pv[e] = pe;
           }
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const float pe = ((allow[c] >> e) & 1u) ? fast_exp2(fmaf(__uint_as_float(sv[e]), p.scale_log2, -m_use)) : 0.f;
+            const float pe = ((allow[c] >> e) & 1u) ? fast_exp2(fmaf(__uint_as_float(x[e]), p.scale_log2, -m_use)) : 0.f;
             l_tile += pe;
             pv[e] = pe;
           }
@@ -241,23 +262,26 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars[6]));
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
-      if (j + 1 < n_tiles) tile_masks(j + 1, allow, keep);       // overlaps the P_j V_j MMAs
-      // O = alpha * O + P_j V_j
-      mbar_wait(smem_u32(&bars[7]), j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c * 32 + e] = fmaf(o[c * 32 + e], alpha, __uint_as_float(ov[e]));
-      }
+      mbar_arrive(smem_u32(&bars[6]));             // P_j written, S_j consumed, O rescaled: P_j V_j (then S_{j+1}) may issue
+      l_run += l_tile;
+      if (j + 1 < n_tiles) tile_masks(j + 1, allow, keep);       // overlaps the P_j V_j and Q K_{j+1} MMAs
     }
-    tc_fence_before();
     if (row_ok) {
+      float o[AT_D];
+      if (n_tiles > 0) {
+        mbar_wait(smem_u32(&bars[7]), 0);          // every P_j V_j has been accumulated
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[c * 32 + e] = __uint_as_float(ov[e]);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+      }
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       if (p.out_dtype == PKA_BF16) {
         __nv_bfloat16* dst = (__nv_bfloat16*)p.out + ((long long)b * p.Lq + i) * p.ldo + h * AT_D;
@@ -276,8 +300,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           *reinterpret_cast<float4*>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
       }
       // natural-log lse of the scaled scores, as the SIMT kernels store it
-      p.lse[((long long)b * p.H + h) * p.Lq + i] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.69314718055994531f : -CUDART_INF_F;
+      p.lse[((long long)b * p.H + h) * p.Lq + i] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.69314718055994531f : -CUDART_INF_F;
+    } else if (n_tiles > 0) {
+      mbar_wait(smem_u32(&bars[7]), 0);            // nobody leaves while the tensor core still writes this CTA's TMEM
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();

@@ -100,26 +100,55 @@ dp_adam_kernel(DpPeers peers, float* param_mc, const float* grad_mc, uint32_t* c
   const long long per = (n >> 2) / world;                    // float4 groups per rank (n % (4*world) == 0)
   const long long lo = per * rank;
   float* p_own = peers.param[rank];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = lo + i;
-    float4 gv;
-    if (MULTICAST) {
-      gv = multimem_ld_reduce_add(grad_mc + 4 * e);
-    } else {
-      gv = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < world; ++r) {                       // fixed rank order: bit-reproducible
-        const float4 x = reinterpret_cast<const float4*>(peers.grad[r])[e];
-        gv.x += x.x; gv.y += x.y; gv.z += x.z; gv.w += x.w;
+  // A peer load is a ~2-3 us round trip over NVLink: every thread keeps kU float4 groups x W ranks of them in flight
+  // (round 1 walked its groups one at a time on 32 CTAs: 27 dependent round trips, 90 us for 7 MB on two GPUs).
+  constexpr int kU = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < per; i0 += kU * stride) {
+    float4 gv[kU], mv[kU], vv[kU], pv[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + u * stride;
+      gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < per) {
+        if (MULTICAST) gv[u] = multimem_ld_reduce_add(grad_mc + 4 * (lo + i));
       }
     }
-    float4 mv = reinterpret_cast<float4*>(m)[e], vv = reinterpret_cast<float4*>(v)[e];
-    float4 pv = reinterpret_cast<const float4*>(p_own)[e];
-    upd(gv.x, mv.x, vv.x, pv.x); upd(gv.y, mv.y, vv.y, pv.y); upd(gv.z, mv.z, vv.z, pv.z); upd(gv.w, mv.w, vv.w, pv.w);
-    reinterpret_cast<float4*>(m)[e] = mv; reinterpret_cast<float4*>(v)[e] = vv;
-    if (MULTICAST) {
-      multimem_st(param_mc + 4 * e, pv);
-    } else {
-      for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.param[r])[e] = pv;
+    if (!MULTICAST) {
+      for (int r = 0; r < world; ++r) {                       // fixed rank order: bit-reproducible
+        float4 x[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const long long i = i0 + u * stride;
+          x[u] = i < per ? __ldcg(reinterpret_cast<const float4*>(peers.grad[r]) + lo + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { gv[u].x += x[u].x; gv[u].y += x[u].y; gv[u].z += x[u].z; gv[u].w += x[u].w; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < per) {
+        const long long e = lo + i;
+        mv[u] = reinterpret_cast<float4*>(m)[e]; vv[u] = reinterpret_cast<float4*>(v)[e];
+        pv[u] = reinterpret_cast<const float4*>(p_own)[e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < per) {
+        const long long e = lo + i;
+        upd(gv[u].x, mv[u].x, vv[u].x, pv[u].x); upd(gv[u].y, mv[u].y, vv[u].y, pv[u].y);
+        upd(gv[u].z, mv[u].z, vv[u].z, pv[u].z); upd(gv[u].w, mv[u].w, vv[u].w, pv[u].w);
+        reinterpret_cast<float4*>(m)[e] = mv[u]; reinterpret_cast<float4*>(v)[e] = vv[u];
+        if (MULTICAST) {
+          multimem_st(param_mc + 4 * e, pv[u]);
+        } else {
+          for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.param[r])[e] = pv[u];
+        }
+      }
     }
   }
   // B: every thread's parameter stores precede the release of the flags
@@ -141,7 +170,7 @@ using namespace pka;
 extern "C" int pka_dp_adam_grid(int64_t n, int world, int max_ctas) {
   if (n <= 0 || world <= 0 || max_ctas <= 0) return 0;
   const long long per = (n / 4) / world;
-  long long ctas = (per + 256 * 4 - 1) / (256 * 4);           // ~4 float4 groups per thread
+  long long ctas = (per + 256 * 2 - 1) / (256 * 2);           // ~2 float4 groups per thread: latency, not bandwidth, bounds it
   if (ctas < 1) ctas = 1;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas > kNumSMs) ctas = kNumSMs;

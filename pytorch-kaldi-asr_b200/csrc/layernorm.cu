@@ -257,7 +257,8 @@ static int fwd_t(const void* x, const void* res, const float* a, const float* b,
                  int rows, int D, float eps, const pka_dropout& dr, cudaStream_t st) {
   dim3 grid((rows + kLnWarps - 1) / kLnWarps), block(kLnWarps * 32);
 #define LN_FWD(E, V) launch_k(add_ln_fwd_kernel<T, E, V>, grid, block, 0, st, (const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
-  if (sizeof(T) == 2 && D % 8 == 0) {             // bf16: 8 elements (16 bytes) per lane and vector
+  if (sizeof(T) == 2 && D % 8 == 0 && D > 128) {  // bf16: 8 elements (16 bytes) per lane and vector (D <= 128 would
+                                                  // leave half of the warp idle: 4 elements per lane there)
     constexpr int E = sizeof(T) == 2 ? 8 : 4;
     const int vpl = (D + 255) / 256;
     if (vpl <= 1) LN_FWD(E, 1); else if (vpl <= 2) LN_FWD(E, 2); else LN_FWD(E, 4);
@@ -276,7 +277,7 @@ static int bwd_t(const void* dy, const void* x, const void* res, const float* a,
   const int nblk = pka_ln_bwd_blocks(rows);
   dim3 grid(nblk), block(kLnWarps * 32);
 #define LN_BWD(E, V) launch_k(add_ln_bwd_kernel<T, E, V>, grid, block, 0, st, (const T*)dy, (const T*)x, (const T*)res, a, mean, rinv, (T*)dx, (T*)dres, ws, rows, D, eps, dr)
-  if (sizeof(T) == 2 && D % 8 == 0) {
+  if (sizeof(T) == 2 && D % 8 == 0 && D > 128) {
     constexpr int E = sizeof(T) == 2 ? 8 : 4;
     const int vpl = (D + 255) / 256;
     if (vpl <= 1) LN_BWD(E, 1); else LN_BWD(E, 2);

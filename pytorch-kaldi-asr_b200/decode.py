@@ -256,8 +256,11 @@ def translate_batch(model, batch, opt, model_options=None):
         if not torch.is_tensor(batch[2]) else batch[2].to(dev, torch.uint8, non_blocking=True)
     with torch.no_grad():
         enc_output, fmask = model.encode(src, mask)
+    # the captured step graph holds raw pointers to the decoder weights: the storage fingerprint makes a model whose
+    # parameters moved (FusedAdam arena, .to(), dtype change) build a fresh decoder instead of replaying stale addresses
+    fingerprint = hash(tuple(p.data_ptr() for p in model.decoder.parameters()))
     key = (id(model), enc_output.shape[0], enc_output.shape[1], opt.beam_size, opt.max_token_seq_len,
-           bool(getattr(opt, "force_full_length", False)), bool(getattr(opt, "use_graph", True)))
+           bool(getattr(opt, "force_full_length", False)), bool(getattr(opt, "use_graph", True)), fingerprint)
     bd = _DECODERS.get(key)
     if bd is None:
         if len(_DECODERS) > 8:

@@ -102,6 +102,7 @@ def gemm(A, B, Cout, M, N, K, *, nseg=1, nbatch=1, lda, ldb, ldc, transA=False, 
 # zero_grad) adopts that view instead of adding into a zeroed buffer -- no per-parameter `grad += g` kernels, no
 # arena memset.  Without a FusedAdam (or when p.grad already holds something to accumulate into) a plain buffer is used.
 _GRAD_SLOTS = {}
+_SLOT_CLAIMS = set()          # arena slots handed out since the last forward pass (see grad_buffer)
 
 
 def register_grad_slots(optimizer):
@@ -120,8 +121,13 @@ def grad_buffer(param_like: torch.Tensor, shape=None) -> torch.Tensor:
         if opt is not None:
             p = opt._train[ent[1]]
             if p.grad is None and p.data_ptr() == param_like.data_ptr() and p.numel() == param_like.numel():
-                off = opt._offsets[ent[1]]
-                return opt.flat_grad[off:off + p.numel()].view(shape)
+                # a parameter that feeds two autograd nodes (tied weights, a module called twice) asks twice in one
+                # backward pass: only the first request gets the slot, the second a plain buffer that autograd adds
+                claim = (id(opt), ent[1])
+                if claim not in _SLOT_CLAIMS:
+                    _SLOT_CLAIMS.add(claim)
+                    off = opt._offsets[ent[1]]
+                    return opt.flat_grad[off:off + p.numel()].view(shape)
     return torch.empty(shape, device=param_like.device, dtype=torch.float32)
 
 
@@ -199,6 +205,7 @@ def reset_deferred():
         d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
     _COLSUM_HINTS.clear()
     _PACKS.clear()
+    _SLOT_CLAIMS.clear()
 
 
 # LayerNorm backward also leaves the column sums of the gradient it hands to the layer below (its dx) as partial rows in

@@ -63,6 +63,10 @@ def main(argv=None):
             raise ValueError('[ERROR] -resume: {} holds no optimiser state'.format(opt.load_model_file))
         checkpoint.restore_optimizer(optimizer, loaded['optimizer'], model)
         opt.start_epoch = int(loaded['epoch']) + 1
+        opt.resume_extra = dict(loaded.get('extra') or {})
+        best_file = os.path.join(opt.save_model_dir, 'epoch.{}.torch'.format(opt.resume_extra.get('best_epoch', 0)))
+        if opt.resume_extra.get('best_epoch', 0) > 0 and os.path.exists(best_file):
+            opt.resume_extra['best_state'] = checkpoint.read_checkpoint(best_file)['state_dict']
     grad_sync = None
     if world > 1 and opt.dp_backend == 'peer':
         optimizer.optimizer.enable_peer_step()

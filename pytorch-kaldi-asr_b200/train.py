@@ -433,7 +433,9 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
     -> (best_accu, best_epoch).
 
     Differences: checkpoints are state-dict files with optimiser / schedule / dropout state (checkpoint.py), so a run
-    can resume bit-exactly; the best model is a *snapshot* taken at its epoch (the reference keeps a reference to the
+    can resume at an epoch boundary with the same weights, optimiser / schedule / dropout state, epoch-shuffle RNG and
+    best-so-far accuracy (the best *weights* of an earlier epoch are re-read from that epoch's checkpoint when it still
+    exists); the best model is a *snapshot* taken at its epoch (the reference keeps a reference to the
     live module, L/train.py:243-245, and therefore saves the last epoch's weights under the best epoch's name).
     Data parallel: every rank calls this with its shard of `train_data` and `grad_sync`; `writer` is True on one rank.
     Like the reference, every evaluation stops after `batch_eval` = 10 batches (L/train.py:127,209-212)."""
@@ -441,6 +443,13 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
     from . import checkpoint as _ckpt
     start_all, best_epoch, best_accu, best_state = time.time(), 0, 0.0, None
     first = int(getattr(opt, 'start_epoch', 1))
+    resumed = getattr(opt, 'resume_extra', None) or {}
+    if resumed:                                   # -resume: the epoch shuffles and the best-so-far continue where they stopped
+        best_accu, best_epoch = float(resumed.get('best_accu', 0.0)), int(resumed.get('best_epoch', 0))
+        best_state = resumed.get('best_state')
+        rng_state = resumed.get('loader_rng')
+        if rng_state is not None and hasattr(train_data, 'set_rng_state'):
+            train_data.set_rng_state(rng_state)
     for epoch in range(first, opt.epoch + 1):
         print('[INFO] trainning epoch {}.'.format(epoch))
         start = time.time()
@@ -471,7 +480,10 @@ def train(model, train_data, dev_data, test_data, crit, optimizer, opt, model_op
             inner.sync_moments()                      # peer mode shards the Adam moments: gather them (all ranks)
         if writer and due:
             model_name = opt.save_model_dir + '/epoch.{}.torch'.format(epoch)
-            _ckpt.save_checkpoint(model_name, model, model_options, epoch, train_options=opt, optimizer=optimizer)
+            extra = dict(best_accu=float(best_accu), best_epoch=int(best_epoch))
+            if hasattr(train_data, 'get_rng_state'):
+                extra['loader_rng'] = train_data.get_rng_state()
+            _ckpt.save_checkpoint(model_name, model, model_options, epoch, train_options=opt, optimizer=optimizer, extra=extra)
             print('[INFO] checkpoint of epoch {} is saved to {}'.format(epoch, model_name))
     print('[INFO] trainning finish.\n\ttime consume: {:3.2f} minute\n\tbest valid accuracy: {:3.2f} %, on epoch {}'
           .format((time.time() - start_all) / 60, 100 * best_accu, best_epoch))

@@ -59,7 +59,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._done = torch.zeros(1, device=dev, dtype=torch.int32)            # CTA-completion counter of the fused step
 
     # ---- data parallel: gradient reduce-scatter + Adam + parameter all-gather in one kernel over peer memory ----
-    def enable_peer_step(self, group=None, max_ctas: int = 32, multicast=None):
+    def enable_peer_step(self, group=None, max_ctas: int = 148, multicast=None):
         """Move the parameter and gradient arenas into NVLink symmetric memory (the same allocation mapped on every
         rank of `group`) and make `step()` one `pka_dp_adam_step` launch per rank: the gradients of all ranks are summed
         while being read (through the switch when NVLS multicast is available), this rank updates its 1/W shard and
@@ -228,6 +228,8 @@ class FusedAdam(torch.optim.Optimizer):
         """Default: drop the .grad references (no kernel at all).  The next backward writes every gradient straight into
         its arena slot and autograd adopts those views; `step()` zero-fills the slot of any parameter that got none.
         set_to_none=False keeps torch's classic behaviour (one memset of the arena, gradients accumulate into it)."""
+        from .. import ops as _ops
+        _ops._SLOT_CLAIMS.clear()                 # a new backward pass may claim every arena slot again
         if set_to_none:
             for p in self._train:
                 p.grad = None

@@ -137,6 +137,20 @@ class BatchLoader:
         m = self.pad_multiple
         return (t + m - 1) // m * m
 
+    # ------------------------------------------------------------------------------------------------ resume
+    def get_rng_state(self):
+        """State of the epoch-shuffle generator plus the current (cumulatively shuffled) order -- what a checkpoint needs
+        for the next epoch's permutation to be the one an uninterrupted run would draw."""
+        state = self._rng.getstate() if hasattr(self._rng, 'getstate') else None
+        return dict(rng=state, order=list(self._order))
+
+    def set_rng_state(self, state):
+        if state.get('rng') is not None and hasattr(self._rng, 'setstate'):
+            rng = state['rng']
+            self._rng.setstate((rng[0], tuple(rng[1]), rng[2]) if isinstance(rng, (list, tuple)) else rng)
+        if state.get('order') is not None and len(state['order']) == len(self._order):
+            self._order[:] = list(state['order'])
+
     # ------------------------------------------------------------------------------------------------ epoch plan
     def __len__(self):
         rank, world = self.shard

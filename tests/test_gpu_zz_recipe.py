@@ -92,3 +92,38 @@ def test_recipe_end_to_end(tmp_path, capsys):
     assert 0.0 <= wer and line.startswith("%WER") and os.path.exists(root + "/exp/scoring/rescore_10.0_wer")
     assert open(root + "/exp/result.txt").read().startswith("[INFO] best wer presented in file:")
     assert "[PROCEDURE] combining start on best epoch" in capsys.readouterr().out
+
+
+def test_stage_driver_runs_init_train_decode_rescore_score_with_the_reference_layout(tmp_path, capsys):
+    """recipe.run = stages 3-5 of P/run.sh:64-203: exp/model_*/model.init -> epoch.N / combined.* -> decode_{dev,test}/
+    decode.txt, lm.3k.score.txt, scoring/rescore_<w>[_wer], result.txt; a toy LM command exercises the score pipe."""
+    from pytorch_kaldi_asr_b200.recipe import run
+    from pytorch_kaldi_asr_b200.utils import kaldi_ark
+    root = str(tmp_path)
+    os.makedirs(root + "/data/lang")
+    for name, n, seed in (("train_filtered", 16, 1), ("dev_filtered", 6, 2), ("test_filtered", 6, 3)):
+        make_dir(root + "/data", name, n, seed)
+    with open(root + "/data/lang/vocab.txt", "w") as f:
+        for i, w in enumerate(["<blank>", "<unk>", "<s>", "</s>"] + PHONES):
+            f.write("%s %d\n" % (w, i))
+    kaldi_ark.write_mat(root + "/data/lda.mat", (np.random.RandomState(0).randn(25, 26) * 0.1).astype(np.float32))
+    summary = run.main(["-data_dir", root + "/data", "-lang_dir", root + "/data/lang", "-exp_dir", root + "/exp",
+                        "-model_suffix", "_tiny", "-encoder_max_len", "40", "-decoder_max_len", "16", "-decoder_sub_sequence",
+                        "(-5,0)", "-en_layers", "1", "-de_layers", "1", "-en_d_model", "32", "-de_d_model", "32", "-d_k", "16",
+                        "-d_v", "16", "-en_dropout", "0.1", "-de_dropout", "0.1", "-init_seed", "0", "-epoch", "2",
+                        "-batch_size", "4", "-optim_start_lr", "0.002", "-compute_mode", "fp32", "-max_token_seq_len", "12",
+                        "-decode_batch_size", "4", "-beam_size", "4", "-nbest", "2", "-inv_weight_list", "10,20",
+                        "-lm_score_cmd", "awk '{print -NF}'"])
+    model_dir = summary["model_dir"]
+    assert os.path.basename(model_dir).startswith("model_") and model_dir.endswith("_tiny")
+    files = os.listdir(model_dir)
+    assert "model.init" in files and "epoch.2.torch" in files and sum(f.startswith("combined.") for f in files) == 1
+    for name in ("dev", "test"):
+        d = model_dir + "/decode_" + name
+        n_hyp = sum(1 for _ in open(d + "/decode.txt"))
+        assert n_hyp >= 6 and sum(1 for _ in open(d + "/lm.3k.score.txt")) == n_hyp
+        assert sorted(f for f in os.listdir(d + "/scoring")) == ["rescore_10.0", "rescore_10.0_wer", "rescore_20.0", "rescore_20.0_wer"]
+        assert open(d + "/result.txt").read().startswith("[INFO] best wer presented in file:")
+        assert 0.0 <= summary["wer_" + name]
+    out = capsys.readouterr().out
+    assert "[PROCEDURE] decoding dev set" in out and "[INFO] language model score computed." in out
