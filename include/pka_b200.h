@@ -167,6 +167,9 @@ typedef struct {
 int pka_relayout_jobs(const pka_relayout_job* jobs_host, int n_jobs, uint64_t* step_counter, void* stream);
 /* teacher-forcing split of L/train.py:163-165 in one launch: tgt i64[B,L1], mask u8[B,L1] ->
  * tgt_in = tgt[:, :-1], goal = tgt[:, 1:], mask_in = mask[:, :-1]  (contiguous [B, L1-1]) */
+/* y bf16 [rows, Np] = x [rows, N] (fp32 or bf16) with zero columns N..Np-1: makes the gradient of a [.., V = 53] output a
+ * TMA-legal GEMM operand (16-byte row pitch), so the vocabulary projection's backward runs on the tensor cores */
+int pka_pad_cast(const void* x, int dtype, void* y, int64_t rows, int N, int Np, void* stream);
 int pka_split_targets(const int64_t* tgt, const uint8_t* mask, int64_t* tgt_in, int64_t* goal, uint8_t* mask_in, int B,
                       int L1, void* stream);
 

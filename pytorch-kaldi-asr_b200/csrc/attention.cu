@@ -310,38 +310,43 @@ attn_bwd_dkv_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict_
 //   phase 3  lane = two output columns: out[q][:] += P[q][j] * V[j][:] with coalesced V rows, 8 warps interleave the keys
 // fp32 throughout; rows without an allowed key give 0 / -inf like the generic kernel.
 constexpr int kSqMaxQ = 16;
-template <int D>
+// NQ = queries rounded up to a multiple of 4 (beam 10 -> 12): the score / output loops are fully unrolled over NQ, so a
+// 16-wide instantiation would spend a quarter of its FMAs on padding
+template <int D, int NQ>
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_smallq_kernel(const AttnP p, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                        const uint8_t* __restrict__ kmask, float* __restrict__ out, float* __restrict__ lse, int LkP) {
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                                  // [16][D]
-  float* S = Qs + kSqMaxQ * D;                     // [16][LkP]
-  float* red = S + kSqMaxQ * LkP;                  // [8][16][D]
+  float* S = Qs + NQ * D;                          // [NQ][LkP]
+  float* red = S + NQ * LkP;                       // [8][NQ][D]
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* km = kmask + (long long)b * p.Lk;
   const float* kb = k + (long long)b * p.Lk * p.ldk + h * D;
   const float* vb = v + (long long)b * p.Lk * p.ldv + h * D;
-  for (int e = threadIdx.x; e < kSqMaxQ * D; e += 256) {
+  for (int e = threadIdx.x; e < NQ * D; e += 256) {
     const int qi = e / D, d = e - qi * D;
     Qs[e] = qi < p.Lq ? q[((long long)b * p.Lq + qi) * p.ldq + h * D + d] : 0.f;
   }
   __syncthreads();
   // ---- phase 1: scores
   for (int j = threadIdx.x; j < LkP; j += 256) {
-    float s[kSqMaxQ];
+    float s[NQ];
 #pragma unroll
-    for (int qi = 0; qi < kSqMaxQ; ++qi) s[qi] = 0.f;
+    for (int qi = 0; qi < NQ; ++qi) s[qi] = 0.f;
     const bool ok = j < p.Lk && km[j] != 0;
     if (ok) {
       const float4* kr = reinterpret_cast<const float4*>(kb + (long long)j * p.ldk);
-#pragma unroll 4
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 kv = kr[d4];
+      float4 krow[D / 4];                          // the whole key row in flight before the first FMA
 #pragma unroll
-        for (int qi = 0; qi < kSqMaxQ; ++qi) {
+      for (int d4 = 0; d4 < D / 4; ++d4) krow[d4] = kr[d4];
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kv = krow[d4];
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
           const float4 qv = *reinterpret_cast<const float4*>(Qs + qi * D + d4 * 4);
           s[qi] = fmaf(qv.x, kv.x, s[qi]); s[qi] = fmaf(qv.y, kv.y, s[qi]);
           s[qi] = fmaf(qv.z, kv.z, s[qi]); s[qi] = fmaf(qv.w, kv.w, s[qi]);
@@ -349,11 +354,11 @@ attn_fwd_smallq_kernel(const AttnP p, const float* __restrict__ q, const float* 
       }
     }
 #pragma unroll
-    for (int qi = 0; qi < kSqMaxQ; ++qi) S[qi * LkP + j] = ok ? s[qi] * p.scale : -CUDART_INF_F;
+    for (int qi = 0; qi < NQ; ++qi) S[qi * LkP + j] = ok ? s[qi] * p.scale : -CUDART_INF_F;
   }
   __syncthreads();
   // ---- phase 2: softmax over the keys, one warp per query
-  for (int qi = warp; qi < kSqMaxQ; qi += 8) {
+  for (int qi = warp; qi < NQ; qi += 8) {
     float* row = S + qi * LkP;
     float m = -CUDART_INF_F;
     for (int j = lane; j < LkP; j += 32) m = fmaxf(m, row[j]);
@@ -369,32 +374,45 @@ attn_fwd_smallq_kernel(const AttnP p, const float* __restrict__ q, const float* 
   __syncthreads();
   // ---- phase 3: out = P V
   constexpr int CPL = D / 32;                      // output columns per lane (D = 64 -> 2)
-  float acc[kSqMaxQ][CPL];
+  float acc[NQ][CPL];
 #pragma unroll
-  for (int qi = 0; qi < kSqMaxQ; ++qi)
+  for (int qi = 0; qi < NQ; ++qi)
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[qi][c] = 0.f;
-  for (int j = warp; j < p.Lk; j += 8) {
-    float vv[CPL];
+  // eight V rows of this warp in flight per round (round 2: one row per round left a single load in flight, ~60
+  // dependent round trips per CTA = 37 of the kernel's 40 us); the accumulation order over j is unchanged
+  constexpr int kVU = 8;
+  for (int j0 = warp; j0 < p.Lk; j0 += 8 * kVU) {
+    float vv[kVU][CPL];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) vv[c] = vb[(long long)j * p.ldv + lane * CPL + c];
+    for (int u = 0; u < kVU; ++u) {
+      const int j = j0 + 8 * u;
 #pragma unroll
-    for (int qi = 0; qi < kSqMaxQ; ++qi) {
-      const float pj = S[qi * LkP + j];
+      for (int c = 0; c < CPL; ++c) vv[u][c] = j < p.Lk ? vb[(long long)j * p.ldv + lane * CPL + c] : 0.f;
+    }
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) acc[qi][c] = fmaf(pj, vv[c], acc[qi][c]);
+    for (int u = 0; u < kVU; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < p.Lk) {
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          const float pj = S[qi * LkP + j];
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[qi][c] = fmaf(pj, vv[u][c], acc[qi][c]);
+        }
+      }
     }
   }
 #pragma unroll
-  for (int qi = 0; qi < kSqMaxQ; ++qi)
+  for (int qi = 0; qi < NQ; ++qi)
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) red[(warp * kSqMaxQ + qi) * D + lane * CPL + c] = acc[qi][c];
+    for (int c = 0; c < CPL; ++c) red[(warp * NQ + qi) * D + lane * CPL + c] = acc[qi][c];
   __syncthreads();
   for (int e = threadIdx.x; e < p.Lq * D; e += 256) {
     const int qi = e / D, d = e - qi * D;
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[(w * kSqMaxQ + qi) * D + d];
+    for (int w = 0; w < 8; ++w) t += red[(w * NQ + qi) * D + d];
     out[((long long)b * p.Lq + qi) * p.ldo + h * D + d] = t;
   }
 }
@@ -450,7 +468,8 @@ static bool smallq_ok(const AttnP& p, int D, const void* q, const void* k, const
   if (D != 64 || p.Lq > kSqMaxQ || p.use_band || p.drop.p > 0.f) return false;
   if ((p.ldk & 3) || (p.ldv & 3) || !aligned16(k) || !aligned16(v) || !aligned16(q)) return false;
   *LkP = (p.Lk + 31) / 32 * 32;
-  *smem = (kSqMaxQ * D + kSqMaxQ * *LkP + 8 * kSqMaxQ * D) * (int)sizeof(float);
+  const int nq = (p.Lq + 3) / 4 * 4;
+  *smem = (nq * D + nq * *LkP + 8 * nq * D) * (int)sizeof(float);
   return *smem <= 200 * 1024 && p.Lk >= 64;
 }
 
@@ -459,14 +478,18 @@ static int fwd_t(const AttnP& p, int D, const void* q, const void* k, const void
                  float* lse, float* probs, cudaStream_t st) {
   int LkP = 0, smem = 0;
   if (sizeof(T) == 4 && !probs && smallq_ok(p, D, q, k, v, &LkP, &smem)) {
-    static int smem_set = 0;
-    if (smem > smem_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static bool smem_set = false;
+    if (!smem_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_smallq_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_fwd: cannot opt in to shared memory: %s", cudaGetErrorString(e));
-      smem_set = 200 * 1024;
+      smem_set = true;
     }
-    launch_k(attn_fwd_smallq_kernel<64>, dim3(p.H, p.B), 256, (size_t)smem, st, p, (const float*)q, (const float*)k, (const float*)v, km,
-             (float*)out, lse, LkP);
+#define PKA_SMALLQ(NQ_) launch_k(attn_fwd_smallq_kernel<64, NQ_>, dim3(p.H, p.B), 256, (size_t)smem, st, p, (const float*)q, (const float*)k, (const float*)v, km, (float*)out, lse, LkP)
+    if (p.Lq <= 4) PKA_SMALLQ(4); else if (p.Lq <= 8) PKA_SMALLQ(8); else if (p.Lq <= 12) PKA_SMALLQ(12); else PKA_SMALLQ(16);
+#undef PKA_SMALLQ
     return check_launch("attn_fwd(smallq)");
   }
   dim3 grid((p.Lq + kAttWarps - 1) / kAttWarps, p.H, p.B), block(kAttWarps * 32);

@@ -266,22 +266,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       l_run += l_tile;
       if (j + 1 < n_tiles) tile_masks(j + 1, allow, keep);       // overlaps the P_j V_j and Q K_{j+1} MMAs
     }
-    if (row_ok) {
-      float o[AT_D];
-      if (n_tiles > 0) {
-        mbar_wait(smem_u32(&bars[7]), 0);          // every P_j V_j has been accumulated
-        tc_fence_after();
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane takes part, rows beyond Lq just do not store
+    float o[AT_D];
+    if (n_tiles > 0) {
+      mbar_wait(smem_u32(&bars[7]), 0);            // every P_j V_j has been accumulated
+      tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t ov[32];
-          tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(tmem_O + lane_addr + (uint32_t)(c * 32), ov);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) o[c * 32 + e] = __uint_as_float(ov[e]);
-        }
-      } else {
-#pragma unroll
-        for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+        for (int e = 0; e < 32; ++e) o[c * 32 + e] = __uint_as_float(ov[e]);
       }
+    } else {
+#pragma unroll
+      for (int d = 0; d < AT_D; ++d) o[d] = 0.f;
+    }
+    if (row_ok) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       if (p.out_dtype == PKA_BF16) {
         __nv_bfloat16* dst = (__nv_bfloat16*)p.out + ((long long)b * p.Lq + i) * p.ldo + h * AT_D;
@@ -301,8 +302,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       }
       // natural-log lse of the scaled scores, as the SIMT kernels store it
       p.lse[((long long)b * p.H + h) * p.Lq + i] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.69314718055994531f : -CUDART_INF_F;
-    } else if (n_tiles > 0) {
-      mbar_wait(smem_u32(&bars[7]), 0);            // nobody leaves while the tensor core still writes this CTA's TMEM
     }
     tc_fence_before();
   }
@@ -599,15 +598,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_const
               }
             }
           }
+          // per-column statistics of the 8 columns (MODE 1: two 16-byte broadcast reads instead of 16 scalar ones)
+          float l2v[8], dlv[8];
+          if (MODE == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { l2v[u] = row_lse2; dlv[u] = row_del; }
+          } else {
+            const float4* pl = reinterpret_cast<const float4*>(col_lse + (t & 1) * AB_BN + c * 32 + e);
+            const float4* pd = reinterpret_cast<const float4*>(col_del + (t & 1) * AB_BN + c * 32 + e);
+            const float4 la = pl[0], lb = pl[1], da = pd[0], db = pd[1];
+            l2v[0] = la.x; l2v[1] = la.y; l2v[2] = la.z; l2v[3] = la.w; l2v[4] = lb.x; l2v[5] = lb.y; l2v[6] = lb.z; l2v[7] = lb.w;
+            dlv[0] = da.x; dlv[1] = da.y; dlv[2] = da.z; dlv[3] = da.w; dlv[4] = db.x; dlv[5] = db.y; dlv[6] = db.z; dlv[7] = db.w;
+          }
+          const uint32_t al8 = (allow[c] >> e) & 0xffu;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int col = c * 32 + e + u;
-            const float l2 = MODE == 0 ? row_lse2 : col_lse[(t & 1) * AB_BN + col];
-            const float dl = MODE == 0 ? row_del : col_del[(t & 1) * AB_BN + col];
-            const float pe = ((allow[c] >> (e + u)) & 1u) ? exp2f(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -l2)) : 0.f;
-            const float pmu = ((kb >> u) & 1u) ? pe * dc.scale : 0.f;
+            // MUFU.EX2 directly: exp2(-inf) = +0 covers dead / out-of-range columns (lse = +inf there)
+            float pe = fast_exp2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -l2v[u]));
+            if (al8 != 0xffu) pe = ((al8 >> u) & 1u) ? pe : 0.f;        // groups of 8 fully allowed keys skip the select
+            const float pmu = (dc.p > 0.f) ? (((kb >> u) & 1u) ? pe * dc.scale : 0.f) : pe;
             pm[e + u] = pmu;
-            ds[e + u] = (pmu * __uint_as_float(dv[e + u]) - pe * dl) * p.scale;
+            ds[e + u] = (pmu * __uint_as_float(dv[e + u]) - pe * dlv[u]) * p.scale;
           }
         }
 #pragma unroll

@@ -84,11 +84,14 @@ reduce_jobs_kernel(const __grid_constant__ ReduceTable tab) {
         if (jb.accumulate) { const float4 c = *reinterpret_cast<float4*>(dst); t.x += c.x; t.y += c.y; t.z += c.z; t.w += c.w; }
         *reinterpret_cast<float4*>(dst) = t;
       } else {
-        for (int i = 0; i < left; ++i) dst[i] = jb.accumulate ? dst[i] + tv[i] : tv[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < left) dst[i] = jb.accumulate ? dst[i] + tv[i] : tv[i];
       }
     } else {
       // PKA_REDUCE_HEADS: src index e = (h*dk + j)*D + d  (one packed head block [(h,j), d])  ->  dst[(h*D + d)*dk + j]
-      for (int i = 0; i < left; ++i) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i >= left) break;
         const long long e = e0 + i;
         const int d = (int)(e % jb.D);
         const int n = (int)(e / jb.D);
@@ -163,9 +166,33 @@ __global__ void split_targets_kernel(const long long* __restrict__ tgt, const ui
   }
 }
 
+// [rows, N] fp32 or bf16 -> bf16 [rows, Np] with the columns N..Np-1 zero: the gradient of an output whose width is not
+// a multiple of 8 (the vocabulary projection, V = 53) as a TMA-legal operand (16-byte row pitch) of the tensor-core GEMMs
+template <typename T>
+__global__ void pad_cast_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int N, int Np) {
+  pdl_wait();
+  const long long total = rows * Np;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Np;
+    const int c = (int)(e - r * Np);
+    y[e] = c < N ? __float2bfloat16_rn(to_f(x[r * N + c])) : __float2bfloat16_rn(0.f);
+  }
+}
+
 }  // namespace pka
 
 using namespace pka;
+
+extern "C" int pka_pad_cast(const void* x, int dtype, void* y, int64_t rows, int N, int Np, void* stream) {
+  PKA_REQUIRE(x && y && rows > 0 && N > 0 && Np >= N, PKA_EINVAL, "pad_cast: bad arguments");
+  const long long total = rows * Np;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
+  if (dtype == PKA_F32) launch_k(pad_cast_kernel<float>, (int)blocks, 256, 0, as_stream(stream), (const float*)x, (__nv_bfloat16*)y, (long long)rows, N, Np);
+  else if (dtype == PKA_BF16) launch_k(pad_cast_kernel<__nv_bfloat16>, (int)blocks, 256, 0, as_stream(stream), (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (long long)rows, N, Np);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "pad_cast: dtype %d", dtype);
+  return check_launch("pad_cast");
+}
 
 extern "C" int pka_split_targets(const int64_t* tgt, const uint8_t* mask, int64_t* tgt_in, int64_t* goal, uint8_t* mask_in,
                                  int B, int L1, void* stream) {

@@ -196,7 +196,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& mapA, const CUte
         }
         if (p.addend && valid) {
           const __nv_bfloat16* ar = p.addend + m * p.ld_add + nb;
-#pragma unroll 4
+#pragma unroll
           for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __bfloat162float(ar[j]);
         }
         if (valid) {

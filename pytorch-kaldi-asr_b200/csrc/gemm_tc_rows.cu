@@ -363,8 +363,8 @@ gemm_tc_rows2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(ah[k]); v[g * 8 + 2 * k] += f.x; v[g * 8 + 2 * k + 1] += f.y; }
               }
-            } else {
-#pragma unroll 4
+            } else {                               // (fully unrolled: a rolled loop would index v[] dynamically and
+#pragma unroll                                   //  push the whole accumulator row into local memory)
               for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __bfloat162float(ar[j]);
             }
           }

@@ -147,9 +147,43 @@ class _Deferred:
     def __init__(self):
         self.lock = threading.Lock()
         self.wgrads, self.jobs, self.keep, self.queued = [], [], [], False
+        self.side = {}               # device index -> side stream for work that is off the backward pass's critical path
+        self.side_used = None        # the side stream that has work in flight since the last flush
 
 
 _DEFER = _Deferred()
+# Work nothing in the backward pass waits for (the full-wave TDNN weight-gradient GEMMs, the embedding scatter-add) runs
+# on a side stream next to the data-gradient chain instead of in line with it; flush_deferred() joins it before the
+# reductions.  Inside a CUDA-graph capture this becomes a fork / join of the graph.  PKA_SIDE=0 keeps one stream.
+SIDE_ENABLED = os.environ.get("PKA_SIDE", "1") != "0"
+
+
+class _SideStream:
+    """`with _SideStream(*tensors_kept_alive):` -- the body's launches go to the side stream, ordered after everything
+    already enqueued on the current stream.  Falls through to the current stream when no flush is scheduled."""
+
+    def __init__(self, *keep):
+        self.keep, self.ctx = keep, None
+
+    def __enter__(self):
+        if not (SIDE_ENABLED and _DEFER.queued):
+            return self
+        cur = torch.cuda.current_stream()
+        side = _DEFER.side.get(cur.device_index)
+        if side is None:
+            side = _DEFER.side[cur.device_index] = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)
+        with _DEFER.lock:
+            _DEFER.side_used = side
+            _DEFER.keep.append(self.keep)         # operands stay allocated until the join
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _defer_schedule() -> bool:
@@ -187,8 +221,10 @@ def flush_deferred():
     leaves, and defensively by FusedAdam.step()."""
     d = _DEFER
     with d.lock:
-        wg, jobs, keep = d.wgrads, d.jobs, d.keep
-        d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
+        wg, jobs, keep, side = d.wgrads, d.jobs, d.keep, d.side_used
+        d.wgrads, d.jobs, d.keep, d.queued, d.side_used = [], [], [], False, None
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)           # join: the side stream's partials feed the sums below
     if wg:
         arr = (L.TcDesc * len(wg))(*wg)
         L.check(L.lib().pka_gemm_tc_wgrad_group(arr, len(wg), L.stream_ptr()), "gemm_tc_wgrad_group")
@@ -202,7 +238,7 @@ def reset_deferred():
     """Drop anything a failed backward pass may have left behind (called at the start of a forward pass)."""
     d = _DEFER
     with d.lock:
-        d.wgrads, d.jobs, d.keep, d.queued = [], [], [], False
+        d.wgrads, d.jobs, d.keep, d.queued, d.side_used = [], [], [], False, None
     _COLSUM_HINTS.clear()
     _PACKS.clear()
     _SLOT_CLAIMS.clear()
@@ -781,8 +817,10 @@ class _EmbedPosFn(torch.autograd.Function):
         B, Ln = tok.shape
         dout = dout.contiguous()
         demb = grad_buffer(emb)                                      # every row is written by the kernel
-        L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.dtype_code(dout), B, Ln, D, V, padding_idx,
-                                      _byref_drop(drop), L.stream_ptr()), "embed_bwd")
+        _defer_schedule()
+        with _SideStream(tok, dout):              # nothing downstream in the backward pass reads the embedding gradient
+            L.check(L.lib().pka_embed_bwd(L.ptr(tok), L.ptr(dout), L.ptr(demb), L.dtype_code(dout), B, Ln, D, V, padding_idx,
+                                          _byref_drop(drop), L.stream_ptr()), "embed_bwd")
         return None, demb, None, None, None, None
 
 
@@ -962,9 +1000,12 @@ class OperandCache:
             ent["seen"] = self.epoch
         if ent is None:
             dev = weight.device
+            # data-gradient operand [K, N]: its row pitch must be a multiple of 16 bytes for TMA, so an output width
+            # that is not a multiple of 8 (V = 53) gets zero columns up to the next one (single-segment layers only)
+            Np = (N + 7) // 8 * 8 if nseg == 1 else N
             ent = dict(params=[weight], wf=torch.empty(N, nseg * K, device=dev, dtype=torch.bfloat16),
-                       wd=torch.empty(K, nseg * N, device=dev, dtype=torch.bfloat16),
-                       spec=[(L.RELAYOUT_PLAIN, N, K, nseg, nseg * K, nseg * N, 0)], seen=self.epoch)
+                       wd=torch.zeros(K, nseg * Np, device=dev, dtype=torch.bfloat16),
+                       spec=[(L.RELAYOUT_PLAIN, N, K, nseg, nseg * K, nseg * Np, 0)], seen=self.epoch)
             self.entries[key] = ent
             self._table = None
             self._relayout_now(ent)
@@ -1061,7 +1102,8 @@ def gemm_tc_rows(A, Bw, Bt, T, N, K, *, nseg=1, lda, ldb, a_seg_col=0, b_seg_col
     return Cout
 
 
-def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, reduce=True, defer=False, heads=None):
+def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, reduce=True, defer=False, heads=None,
+                  m_valid=None):
     """mode 2: dW[o, seg*N+i] = sum_{b,t} dZ[b,t,o] * X[b,t+shift[seg],i] -> fp32 [M, nseg*N], straight from the row-major
     activations (MN-major UMMA operands; the frame shift is a TMA row coordinate).  The reduction over all frames is
     split over the utterances to fill the SMs; partial sums are added in a fixed order (deterministic).
@@ -1099,6 +1141,9 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, re
         with _DEFER.lock:
             _DEFER.wgrads.append(d)
             _DEFER.keep.append((dZ, X, ws))
+    elif deferred:                                # a full-wave GEMM nobody waits for: next to the data-gradient chain
+        with _SideStream(dZ, X, ws):
+            L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
     else:
         L.check(L.lib().pka_gemm_tc(C.byref(d), L.stream_ptr()), "gemm_tc(wgrad)")
     per = M * nseg * N
@@ -1128,12 +1173,15 @@ def gemm_tc_wgrad(dZ, X, Bt, T, M, N, nseg, shift, out=None, accumulate=None, re
     if not reduce:
         return ws, splits                         # the caller sums the split partials itself (fused with its relayout)
     acc = (out is not None) if accumulate is None else bool(accumulate)
+    n_out = per if m_valid is None else m_valid * nseg * N          # rows beyond m_valid are zero padding of dZ
     if out is None:
-        out = torch.empty(M, nseg * N, device=dZ.device, dtype=torch.float32)
+        out = torch.empty(n_out // (nseg * N), nseg * N, device=dZ.device, dtype=torch.float32)
     if deferred:
-        defer_reduce(ws, out, per, splits, per, accumulate=acc)
+        defer_reduce(ws, out, n_out, splits, per, accumulate=acc)
     else:
-        L.check(L.lib().pka_tc_reduce(L.ptr(ws), L.ptr(out), C.c_int64(per), splits, int(acc), L.stream_ptr()), "tc_reduce")
+        j = L.ReduceJob()
+        j.src, j.dst, j.n, j.split_stride, j.splits, j.kind, j.accumulate = ws.data_ptr(), out.data_ptr(), n_out, per, splits, 0, int(acc)
+        L.check(L.lib().pka_reduce_jobs(C.byref(j), 1, L.stream_ptr()), "reduce_jobs")
     return out
 
 
@@ -1190,6 +1238,8 @@ class _LinearTcFn(torch.autograd.Function):
         needs_dx = ctx.needs_input_grad[0]
         if OPERANDS is not None and weight.is_contiguous():
             wf, wd = OPERANDS.plain(weight, N, kin, n_ctx)         # refreshed once per forward pass, not per op
+        elif N % 8 != 0 and n_ctx == 1 and weight.is_contiguous():
+            wf, wd = OperandCache().plain(weight, N, kin, 1)       # one-off entry: zero-padded data-gradient operand
         else:
             wf, wd = weight_relayout(w2.detach(), kin, n_ctx, True, needs_dx)
         if link is not None:
@@ -1225,20 +1275,28 @@ class _LinearTcFn(torch.autograd.Function):
                 L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(tmp), L.dtype_code(dy), C.c_int64(dy.numel()),
                                                 _byref_drop(drop), L.stream_ptr()), "dropout_bwd")
                 dy = tmp
-            if dy.dtype == torch.bfloat16:
-                dz = dy
+            if dy.dtype == torch.bfloat16 or N % 8 != 0:
+                dz = dy                           # (N % 8 != 0: converted and zero-padded below)
             elif want_db and N % 4 == 0:          # fp32 -> bf16 copy and bias gradient in one pass
                 dz, db = gate_colsum(dy, None, 1.0, bias, Bt, T, N, defer=True)
                 want_db = False
             else:
                 dz = gate_to_bf16(dy, Bt, T, N)
         addend = ctx.link.take() if ctx.link is not None else None       # residual-branch gradient of the sub-layer input
+        Np = N
+        if N % 8 != 0:                            # V = 53: zero-pad the gradient to a TMA-legal width (wd is padded alike)
+            assert n_ctx == 1 and wd.shape[1] % 8 == 0 and not has_bias
+            Np = wd.shape[1]
+            dzp = torch.empty(Bt, T, Np, device=dy.device, dtype=torch.bfloat16)
+            L.check(L.lib().pka_pad_cast(L.ptr(dy), L.dtype_code(dy), L.ptr(dzp), C.c_int64(Bt * T), N, Np, L.stream_ptr()),
+                    "pad_cast")
+            dz = dzp
         if ctx.needs_input_grad[0]:
-            dx = gemm_tc_rows(dz, wd, Bt, T, kin, N, nseg=n_ctx, lda=N, ldb=n_ctx * N, b_seg_col=N,
+            dx = gemm_tc_rows(dz, wd, Bt, T, kin, Np, nseg=n_ctx, lda=Np, ldb=n_ctx * Np, b_seg_col=Np,
                               shift=[-c for c in splice], addend=addend)
         if ctx.needs_input_grad[1]:
-            dw = gemm_tc_wgrad(dz, x, Bt, T, N, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
-                               accumulate=False, defer=True).view(wshape)
+            dw = gemm_tc_wgrad(dz, x, Bt, T, Np, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
+                               accumulate=False, defer=True, m_valid=N).view(wshape)
         if want_db:
             hint = _COLSUM_HINTS.pop(dz.data_ptr(), None) if dz is dy else None
             if hint is not None and hint[2] == Bt * T and hint[3] == N and _defer_schedule():

@@ -181,9 +181,9 @@ class Decoder(nn.Module):
             slf_attns.append(a1)
             enc_attns.append(a2)
         x = ops.add_pos_dropout(x, None, self._rng.make(self.p, self._site_out, dev, self.training))
-        # V = 53 columns do not meet TMA's 16-byte row pitch for the data-gradient operand: the vocabulary projection
-        # (0.3 % of the step's FLOPs) stays on the fp32 GEMM and hands fp32 logits to the loss
-        logits = self.tgt_word_proj(ops.cast(x, torch.float32))
+        # fp32 logits for the loss.  bf16 path: tensor-core GEMM with fp32 output; V = 53 does not meet TMA's 16-byte row
+        # pitch as a data-gradient operand, so the backward zero-pads the logit gradient to 56 columns (ops.linear_tc)
+        logits = self.tgt_word_proj(x, out_fp32=True) if x.dtype == torch.bfloat16 else self.tgt_word_proj(x)
         return (logits, slf_attns, enc_attns) if return_attns else (logits,)
 
 

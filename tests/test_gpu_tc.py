@@ -42,6 +42,7 @@ def rnd(*shape, seed=0, scale=1.0):
     (4, 300, 512, 128, None, False, True),       # 8 resident K blocks but only 4 weight stages (hung in round 2 before the
                                                  # activation producer issued four blocks per turn)
     (2, 200, 128, 768, None, False, False),      # fused cross-attention k|v of three layers: 256 columns per CTA, 3 grid rows
+    (4, 63, 128, 53, None, False, False),        # vocabulary projection: V = 53, the backward zero-pads the gradient to 56
 ])
 def test_linear_tc_fwd_bwd(Bt, T, kin, N, ctx, relu, bias):
     from pytorch_kaldi_asr_b200 import ops

@@ -24,12 +24,12 @@ def run(name, B, H, Lq, Lk, band, p_drop, d_model):
         i[0] += 1
         with torch.no_grad():
             ops.attention_tc(q[i[0] % 4], kv[i[0] % 4], mask, H, 64, band, 1.0 / math.sqrt(d_model), drop)
-    outs = [ops.attention_tc(q[k], kv[k], mask, H, 64, band, 1.0 / math.sqrt(d_model), drop)[0] for k in range(4)]
-    def bwd():
-        i[0] += 1
-        outs[i[0] % 4].backward(gy, retain_graph=True)
+    def both():                                   # forward + backward inside one capture (autograd replays the backward
+        i[0] += 1                                 # on the forward's stream, which must be the capturing one)
+        out, _ = ops.attention_tc(q[i[0] % 4], kv[i[0] % 4], mask, H, 64, band, 1.0 / math.sqrt(d_model), drop)
+        out.backward(gy)
     tf = time_kernel(fwd, iters=8, replays=3)
-    tb = time_kernel(bwd, iters=4, replays=3)
+    tb = time_kernel(both, iters=4, replays=3) - tf
     pairs = B * H * (_band_pairs(Lq, Lk, band) if not cross else Lq * Lk)
     fl = pairs * 4.0 * 64
     print("%-34s fwd %8.2f us %7.1f TFLOP/s (%.1f%% of burst) | bwd(dQ + dK/dV) %8.2f us %7.1f TFLOP/s"
