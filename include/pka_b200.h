@@ -234,6 +234,10 @@ int pka_add_layernorm_bwd(const void* dy, const void* x, const void* residual, c
 int pka_ce_blocks(int N);
 int pka_ce_fwd(const void* logits, const int64_t* goal, int dtype, int N, int V, int smoothing, float eps,
                float* out3, float* lse, float* part_ws, void* stream);
+/* the same in ONE launch: the last CTA to finish sums the partials in the same fixed order.  done_counter: uint32[1],
+ * zero before the first call (it resets itself). */
+int pka_ce_fwd_fused(const void* logits, const int64_t* goal, int dtype, int N, int V, int smoothing, float eps,
+                     float* out3, float* lse, float* part_ws, uint32_t* done_counter, void* stream);
 /* dlogits = grad_out[0] * (softmax - target) on non-PAD rows, 0 on PAD rows. */
 int pka_ce_bwd(const void* logits, const int64_t* goal, const float* lse, const float* grad_out, void* dlogits,
                int dtype, int N, int V, int smoothing, float eps, void* stream);

@@ -14,9 +14,10 @@ constexpr int kCeWarps = 8;
 template <typename T>
 __global__ void __launch_bounds__(kCeWarps * 32)
 ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal, int N, int V, int smoothing,
-              float eps, float* __restrict__ lse_o, float* __restrict__ part) {
+              float eps, float* __restrict__ lse_o, float* part, unsigned int* done, float* out3) {
   pdl_wait();
   __shared__ float red[kCeWarps][3];
+  __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float loss = 0.f, correct = 0.f, words = 0.f;
   for (int row = blockIdx.x * kCeWarps + warp; row < N; row += gridDim.x * kCeWarps) {
@@ -65,6 +66,23 @@ ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ goal, 
     for (int w = 0; w < kCeWarps; ++w) s += red[w][threadIdx.x];
     part[blockIdx.x * 3 + threadIdx.x] = s;
   }
+  if (!done) return;
+  // fused finish: the LAST CTA to arrive sums the per-CTA partials in index order (the same fixed order as
+  // ce_finish_kernel, whichever CTA happens to be last), so the separate single-CTA launch disappears
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int k = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (k < 3) {
+    float s = 0.f;
+    for (int b = ln; b < (int)gridDim.x; b += 32) s += __ldcg(part + b * 3 + k);     // L2: written by other SMs
+    s = warp_sum(s);
+    if (ln == 0) out3[k] = s;
+  }
+  if (threadIdx.x == 0) *done = 0u;
 }
 
 __global__ void ce_finish_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out3) {
@@ -118,14 +136,31 @@ extern "C" int pka_ce_fwd(const void* logits, const int64_t* goal, int dtype, in
   const int nblk = pka_ce_blocks(N);
   cudaStream_t st = as_stream(stream);
   if (dtype == PKA_F32)
-    launch_k(ce_fwd_kernel<float>, nblk, kCeWarps * 32, 0, st, (const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+    launch_k(ce_fwd_kernel<float>, nblk, kCeWarps * 32, 0, st, (const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws, (unsigned int*)nullptr, (float*)nullptr);
   else if (dtype == PKA_BF16)
-    launch_k(ce_fwd_kernel<__nv_bfloat16>, nblk, kCeWarps * 32, 0, st, (const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws);
+    launch_k(ce_fwd_kernel<__nv_bfloat16>, nblk, kCeWarps * 32, 0, st, (const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws, (unsigned int*)nullptr, (float*)nullptr);
   else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_fwd: dtype %d", dtype);
   int rc = check_launch("ce_fwd");
   if (rc) return rc;
   launch_k(ce_finish_kernel, 1, 96, 0, st, part_ws, nblk, out3);
   return check_launch("ce_finish");
+}
+
+// pka_ce_fwd with the fixed-order finish done by the last CTA of the same launch.  done_counter: uint32[1], zero before
+// the first call (resets itself); one counter per stream that may run the loss concurrently.
+extern "C" int pka_ce_fwd_fused(const void* logits, const int64_t* goal, int dtype, int N, int V, int smoothing, float eps,
+                                float* out3, float* lse, float* part_ws, uint32_t* done_counter, void* stream) {
+  using namespace pka;
+  PKA_REQUIRE(logits && goal && out3 && lse && part_ws && done_counter, PKA_EINVAL, "ce_fwd_fused: null pointer");
+  PKA_REQUIRE(N > 0 && V > 1, PKA_EINVAL, "ce_fwd_fused: N=%d V=%d", N, V);
+  const int nblk = pka_ce_blocks(N);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == PKA_F32)
+    launch_k(ce_fwd_kernel<float>, nblk, kCeWarps * 32, 0, st, (const float*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws, (unsigned int*)done_counter, out3);
+  else if (dtype == PKA_BF16)
+    launch_k(ce_fwd_kernel<__nv_bfloat16>, nblk, kCeWarps * 32, 0, st, (const __nv_bfloat16*)logits, (const long long*)goal, N, V, smoothing, eps, lse, part_ws, (unsigned int*)done_counter, out3);
+  else PKA_REQUIRE(false, PKA_EUNSUPPORTED, "ce_fwd_fused: dtype %d", dtype);
+  return check_launch("ce_fwd_fused");
 }
 
 extern "C" int pka_ce_bwd(const void* logits, const int64_t* goal, const float* lse, const float* grad_out,

@@ -241,6 +241,7 @@ def reset_deferred():
         d.wgrads, d.jobs, d.keep, d.queued, d.side_used = [], [], [], False, None
     _COLSUM_HINTS.clear()
     _PACKS.clear()
+    _IN_DROP.clear()
     _SLOT_CLAIMS.clear()
 
 
@@ -641,6 +642,19 @@ def attention_tc(qbuf, kvbuf, key_mask, n_head: int, d_k: int, band, scale: floa
 _PACKS = {}           # address of a column-block view -> GradPack of its base (cleared at every forward pass)
 
 
+class _DropRec:
+    """A dropout whose output feeds exactly one tensor-core linear layer: that layer applies the keep mask in the epilogue
+    of its data-gradient GEMM (the mask is a pure function of the element index, and dX has the index space of the
+    dropout's output), so the dropout's own backward kernel disappears.  `fused` is set by the consuming layer."""
+    __slots__ = ("drop", "fused")
+
+    def __init__(self, drop):
+        self.drop, self.fused = drop, False
+
+
+_IN_DROP = {}         # address of a dropout output with a single linear consumer -> _DropRec (cleared at every forward pass)
+
+
 class GradPack:
     """Gradient side of a packed multi-consumer buffer: every consumer writes its gradient into its own column block of
     ONE buffer shaped like the forward buffer, so the producer's backward sees a single packed gradient."""
@@ -856,7 +870,7 @@ def cast(x, dtype):
 
 class _AddRowvecDropoutFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, rowvec, period, drop):
+    def forward(ctx, x, rowvec, period, drop, single_consumer=False):
         L.require_cuda(x, rowvec)
         x = x.contiguous()
         D = x.shape[-1]
@@ -867,28 +881,33 @@ class _AddRowvecDropoutFn(torch.autograd.Function):
         L.check(L.lib().pka_add_rowvec_dropout_fwd(L.ptr(x), L.ptr(rowvec), L.ptr(out), L.dtype_code(x), C.c_int64(rows), D,
                                                    period, _byref_drop(drop), L.stream_ptr()), "add_rowvec_dropout_fwd")
         ctx.drop = drop
+        ctx.rec = None
+        if single_consumer and drop is not None and drop.on and out.dtype == torch.bfloat16:
+            ctx.rec = _IN_DROP[out.data_ptr()] = _DropRec(drop)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         drop = ctx.drop
-        if drop is None or not drop.on:
-            return dy, None, None, None
+        if drop is None or not drop.on or (ctx.rec is not None and ctx.rec.fused):
+            return dy, None, None, None, None     # (fused: the consuming layer's data-gradient GEMM applied the mask)
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
         L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(dx), L.dtype_code(dy), C.c_int64(dy.numel()), _byref_drop(drop),
                                         L.stream_ptr()), "dropout_bwd")
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def add_pos_dropout(x, pos_table: Optional[torch.Tensor], drop: Optional[Drop] = None):
-    """dropout(x + pos_table[arange(x.size(1))]) (T/Models.py:164-165); pos_table None = plain dropout."""
+def add_pos_dropout(x, pos_table: Optional[torch.Tensor], drop: Optional[Drop] = None, single_consumer: bool = False):
+    """dropout(x + pos_table[arange(x.size(1))]) (T/Models.py:164-165); pos_table None = plain dropout.
+    `single_consumer`: the result feeds exactly one tensor-core linear layer, which may then take over the mask of the
+    backward pass (see _DropRec)."""
     if pos_table is None and (drop is None or not drop.on):
         return x
     period = x.shape[-2]
     if pos_table is not None:
         assert pos_table.shape[0] >= period, "sequence length %d exceeds the position table (%d)" % (period, pos_table.shape[0])
-    return _AddRowvecDropoutFn.apply(x, pos_table, period, drop)
+    return _AddRowvecDropoutFn.apply(x, pos_table, period, drop, single_consumer)
 
 
 # ------------------------------------------------------------------------------------------------ loss
@@ -908,8 +927,12 @@ class _CrossEntropyFn(torch.autograd.Function):
         lse = torch.empty(N, device=logits2d.device, dtype=torch.float32)
         nblk = L.lib().pka_ce_blocks(N)
         ws = torch.empty(3 * nblk, device=logits2d.device, dtype=torch.float32)
-        L.check(L.lib().pka_ce_fwd(L.ptr(logits2d), L.ptr(goal), L.dtype_code(logits2d), N, V, int(smoothing),
-                                   C.c_float(eps), L.ptr(out3), L.ptr(lse), L.ptr(ws), L.stream_ptr()), "ce_fwd")
+        done = _CE_DONE.get(logits2d.device.index)
+        if done is None:                          # zero once; the kernel's last CTA resets it after summing the partials
+            done = _CE_DONE[logits2d.device.index] = torch.zeros(1, device=logits2d.device, dtype=torch.int32)
+        L.check(L.lib().pka_ce_fwd_fused(L.ptr(logits2d), L.ptr(goal), L.dtype_code(logits2d), N, V, int(smoothing),
+                                         C.c_float(eps), L.ptr(out3), L.ptr(lse), L.ptr(ws), L.ptr(done), L.stream_ptr()),
+                "ce_fwd")
         ctx.save_for_backward(logits2d, goal, lse)
         ctx.meta = (int(smoothing), eps)
         loss = out3[0]
@@ -932,6 +955,7 @@ class _CrossEntropyFn(torch.autograd.Function):
 
 
 _CE_OUT = []
+_CE_DONE = {}          # device index -> uint32[1] CTA-completion counter of the loss kernel (self-resetting)
 
 
 def cross_entropy_sum(logits2d, goal, smoothing: bool = False, eps: float = 0.1, out3: Optional[torch.Tensor] = None):
@@ -1227,7 +1251,7 @@ class _LinearTcFn(torch.autograd.Function):
     weight-gradient).  Weights stay fp32 masters; their bf16 operand copies are made here, once per call."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, splice, relu, drop, out_fp32, link=None):
+    def forward(ctx, x, weight, bias, splice, relu, drop, out_fp32, link=None, single_consumer=False):
         L.require_cuda(x, weight, bias)
         assert x.dtype == torch.bfloat16 and x.dim() == 3 and x.is_contiguous()
         Bt, T, kin = x.shape
@@ -1249,6 +1273,16 @@ class _LinearTcFn(torch.autograd.Function):
                          bias=bias, relu=relu, drop=drop, out_dtype=torch.float32 if out_fp32 else torch.bfloat16)
         if relu and GATE_TAP is not None:
             GATE_TAP.append(y)
+        # dropout of the INPUT (applied by the op that produced x) folded into this layer's data-gradient epilogue
+        rec = _IN_DROP.get(x.data_ptr())
+        ctx.in_drop = None
+        if rec is not None and needs_dx:
+            rec.fused = True
+            ctx.in_drop = rec.drop
+        # ... and this layer's own output dropout offered to ITS single consumer (no ReLU: the gate kernel handles that case)
+        ctx.rec = None
+        if single_consumer and not relu and drop is not None and drop.on and y.dtype == torch.bfloat16:
+            ctx.rec = _IN_DROP[y.data_ptr()] = _DropRec(drop)
         ctx.save_for_backward(x, wd, y if relu else None, w2, bias)
         ctx.meta = (Bt, T, kin, N, n_ctx, tuple(splice) if splice else (0,), relu, drop, bias is not None, weight.shape)
         return y
@@ -1270,7 +1304,7 @@ class _LinearTcFn(torch.autograd.Function):
             else:
                 dz = gate_to_bf16(dy, Bt, T, N, y=y, scale=scale)
         else:
-            if use_drop:
+            if use_drop and not (ctx.rec is not None and ctx.rec.fused):
                 tmp = torch.empty_like(dy)
                 L.check(L.lib().pka_dropout_bwd(L.ptr(dy), L.ptr(tmp), L.dtype_code(dy), C.c_int64(dy.numel()),
                                                 _byref_drop(drop), L.stream_ptr()), "dropout_bwd")
@@ -1293,7 +1327,7 @@ class _LinearTcFn(torch.autograd.Function):
             dz = dzp
         if ctx.needs_input_grad[0]:
             dx = gemm_tc_rows(dz, wd, Bt, T, kin, Np, nseg=n_ctx, lda=Np, ldb=n_ctx * Np, b_seg_col=Np,
-                              shift=[-c for c in splice], addend=addend)
+                              shift=[-c for c in splice], addend=addend, drop=ctx.in_drop)
         if ctx.needs_input_grad[1]:
             dw = gemm_tc_wgrad(dz, x, Bt, T, Np, kin, n_ctx, splice, out=grad_buffer(w2, (N, n_ctx * kin)),
                                accumulate=False, defer=True, m_valid=N).view(wshape)
@@ -1304,14 +1338,15 @@ class _LinearTcFn(torch.autograd.Function):
                 defer_reduce(hint[0], db, N, hint[1], 3 * N, src_off=2 * N)
             else:
                 db = colsum(dz.view(Bt * T, N), out=grad_buffer(bias), accumulate=False, defer=True)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 GATE_TAP = None          # parity tests set this to a list: every [ReLU] tensor-core layer appends its output (call order)
 
 
-def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32=False, link: Optional[ResidualLink] = None):
-    return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32, link)
+def linear_tc(x, weight, bias=None, splice=None, relu=False, drop=None, out_fp32=False, link: Optional[ResidualLink] = None,
+              single_consumer: bool = False):
+    return _LinearTcFn.apply(x, weight, bias, list(splice) if splice else None, relu, drop, out_fp32, link, single_consumer)
 
 
 def transpose_to_bf16(weight_kn):

@@ -129,10 +129,13 @@ class EncoderTest(nn.Module):
         x = ops.frontend(src_seq, lengths, fold, self.concat.index, cmvn,
                          out_dtype=torch.bfloat16 if bf16 else torch.float32)
         x = self.lda_layer(x)
-        x = self.src_projection(x, drop=self._rng.make(self.p, self._site_src, dev, self.training))
+        # (single_consumer: the dropped-out projection feeds only TDNN layer 0, whose data-gradient GEMM then applies the
+        #  mask of the backward pass in its epilogue -- likewise for the two dropouts further down)
+        x = self.src_projection(x, drop=self._rng.make(self.p, self._site_src, dev, self.training), single_consumer=True)
         for layer in self.tdnn_stack:
             x = layer(x)
-        return ops.add_pos_dropout(x, self.trans_pos_enc.weight, self._rng.make(self.p, self._site_out, dev, self.training))
+        return ops.add_pos_dropout(x, self.trans_pos_enc.weight, self._rng.make(self.p, self._site_out, dev, self.training),
+                                   single_consumer=True)
 
 
 class Decoder(nn.Module):
@@ -180,7 +183,7 @@ class Decoder(nn.Module):
             x, a1, a2 = layer(x, enc, slf_attn_mask=slf_mask, dec_enc_attn_mask=enc_mask)
             slf_attns.append(a1)
             enc_attns.append(a2)
-        x = ops.add_pos_dropout(x, None, self._rng.make(self.p, self._site_out, dev, self.training))
+        x = ops.add_pos_dropout(x, None, self._rng.make(self.p, self._site_out, dev, self.training), single_consumer=True)
         # fp32 logits for the loss.  bf16 path: tensor-core GEMM with fp32 output; V = 53 does not meet TMA's 16-byte row
         # pitch as a data-gradient operand, so the backward zero-pads the logit gradient to 56 columns (ops.linear_tc)
         logits = self.tgt_word_proj(x, out_fp32=True) if x.dtype == torch.bfloat16 else self.tgt_word_proj(x)

@@ -20,10 +20,11 @@ class Linear(nn.Module):
         self.linear = nn.Linear(d_in, d_out, bias=bias)
         init.xavier_normal_(self.linear.weight)
 
-    def forward(self, x, drop=None, residual=None, out_fp32=False):
+    def forward(self, x, drop=None, residual=None, out_fp32=False, single_consumer=False):
         if x.dtype == torch.bfloat16:          # bf16 training path: tcgen05 GEMMs (ops.set_compute_mode("bf16"))
             assert residual is None
-            return ops.linear_tc(x, self.linear.weight, self.linear.bias, drop=drop, out_fp32=out_fp32)
+            return ops.linear_tc(x, self.linear.weight, self.linear.bias, drop=drop, out_fp32=out_fp32,
+                                 single_consumer=single_consumer)
         return ops.linear(x, self.linear.weight, self.linear.bias, drop=drop, residual=residual)
 
 
