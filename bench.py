@@ -277,13 +277,14 @@ def roofline_probe(model, B, T, pk, mode):
 
 
 def hbm_probe():
-    """The residual-add + LayerNorm forward kernel THE TIMED STEP RUNS (bf16 activation stream:
-    add_ln_fwd_kernel<__nv_bfloat16, 8, 1>), at the step's own shape (B*L = 2016 rows of 128: 1.5 MB, latency-bound) and
+    """The residual-add + LayerNorm forward kernel THE TIMED STEP RUNS (bf16 activation stream, D = 128:
+    add_ln_fwd_kernel<__nv_bfloat16, 4, 1, R>, R = rows per warp), at the step's own shape (B*L = 2016 rows of 128: 1.5 MB, latency-bound) and
     at a bandwidth-sized shape (> L2), CUDA-graph-timed alone.  Algorithmic bytes = 3 * rows * D * 2 (read x, read
     residual, write y)."""
     from pytorch_kaldi_asr_b200 import ops
     pk_ = peaks()
-    out = {"kernel": "add_ln_fwd_kernel<__nv_bfloat16, 8, 1> (dropout(x) + residual -> LayerNormalization, bf16 in/out)",
+    out = {"kernel": "add_ln_fwd_kernel<__nv_bfloat16, 4, 1, R> (dropout(x) + residual -> LayerNormalization, bf16 in/out; "
+                     "R = 1 row per warp at the in-step shape, 4 at the bandwidth-sized one)",
            "bound": "hbm", "peak": pk_["hbm_gbs"], "unit": "GB/s", "peak_source": pk_["source"] + " copy bandwidth"}
     for name, rows, D, nbuf in (("in_step", 2016, 128, 64), ("bandwidth_sized", 32 * 430 * 64, 128, 2)):
         xs = [torch.randn(rows, D, device="cuda").bfloat16() for _ in range(nbuf)]      # in-step: 64 x 0.5 MB rotate

@@ -51,74 +51,85 @@ template <int EV> __device__ __forceinline__ void drop_mulv(const DropCtx& dc, u
 }
 
 // VPL = 16-byte vectors per lane (EV elements each); a row of D <= 32*EV*VPL elements lives in registers.
-template <typename T, int EV, int VPL>
+// RPW = rows per warp: the loads of all RPW rows (x and residual) are issued before the first reduction, so a warp has
+// RPW times the bytes in flight (narrow rows -- D = 128 bf16 is 256 B -- cannot cover the HBM latency one row at a time:
+// 48 % of the copy bandwidth with RPW = 1 at a bandwidth-sized shape, round 2).
+template <typename T, int EV, int VPL, int RPW>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ a,
                   const float* __restrict__ bta, T* __restrict__ y, float* __restrict__ mean_o,
                   float* __restrict__ rinv_o, int rows, int D, float eps, const pka_dropout drop) {
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * kLnWarps + warp;
-  if (row >= rows) return;
+  const int row0 = (blockIdx.x * kLnWarps + warp) * RPW;
+  if (row0 >= rows) return;
   DropCtx dc = make_drop(drop);
-  const T* xr = x + (long long)row * D;
-  const T* rr = res ? res + (long long)row * D : nullptr;
-  float z[VPL][EV];
-  float sum = 0.f;
+  float z[RPW][VPL][EV], rv[RPW][VPL][EV];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * EV;
+  for (int r = 0; r < RPW; ++r) {                  // every load of the warp's rows first
+    const int row = row0 + r;
 #pragma unroll
-    for (int i = 0; i < EV; ++i) z[v][i] = 0.f;
-    if (c < D) {
-      ldv<T, EV>(xr + c, z[v]);
-      if (dc.p > 0.f) {
-        float m[EV];
-        drop_mulv<EV>(dc, (unsigned long long)row * D + c, m);
+    for (int v = 0; v < VPL; ++v) {
+      const int c = (v * 32 + lane) * EV;
 #pragma unroll
-        for (int i = 0; i < EV; ++i) z[v][i] *= m[i];
+      for (int i = 0; i < EV; ++i) { z[r][v][i] = 0.f; rv[r][v][i] = 0.f; }
+      if (c < D && row < rows) {
+        ldv<T, EV>(x + (long long)row * D + c, z[r][v]);
+        if (res) ldv<T, EV>(res + (long long)row * D + c, rv[r][v]);
       }
-      if (rr) {
-        float r[EV];
-        ldv<T, EV>(rr + c, r);
-#pragma unroll
-        for (int i = 0; i < EV; ++i) z[v][i] += r[i];
-      }
-#pragma unroll
-      for (int i = 0; i < EV; ++i) sum += z[v][i];
     }
   }
-  const float mean = warp_sum(sum) / (float)D;
-  float sq = 0.f;
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * EV;
-    if (c < D) {
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    if (row >= rows) break;                        // warp-uniform
+    float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < EV; ++i) { const float d = z[v][i] - mean; sq = fmaf(d, d, sq); }
-    }
-  }
-  const float sigma = sqrtf(warp_sum(sq) / (float)(D - 1));
-  const float rinv = 1.f / (sigma + eps);
-  T* yr = y + (long long)row * D;
+    for (int v = 0; v < VPL; ++v) {
+      const int c = (v * 32 + lane) * EV;
+      if (c < D) {
+        if (dc.p > 0.f) {
+          float m[EV];
+          drop_mulv<EV>(dc, (unsigned long long)row * D + c, m);
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int c = (v * 32 + lane) * EV;
-    if (c < D) {
-      float o[EV];
+          for (int i = 0; i < EV; ++i) z[r][v][i] *= m[i];
+        }
 #pragma unroll
-      for (int i = 0; i < EV; i += 4) {
-        const float4 av = *reinterpret_cast<const float4*>(a + c + i);
-        const float4 bv = *reinterpret_cast<const float4*>(bta + c + i);
-        o[i] = (z[v][i] - mean) * rinv * av.x + bv.x;
-        o[i + 1] = (z[v][i + 1] - mean) * rinv * av.y + bv.y;
-        o[i + 2] = (z[v][i + 2] - mean) * rinv * av.z + bv.z;
-        o[i + 3] = (z[v][i + 3] - mean) * rinv * av.w + bv.w;
+        for (int i = 0; i < EV; ++i) { z[r][v][i] += rv[r][v][i]; sum += z[r][v][i]; }
       }
-      stv<T, EV>(yr + c, o);
     }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = (v * 32 + lane) * EV;
+      if (c < D) {
+#pragma unroll
+        for (int i = 0; i < EV; ++i) { const float d = z[r][v][i] - mean; sq = fmaf(d, d, sq); }
+      }
+    }
+    const float sigma = sqrtf(warp_sum(sq) / (float)(D - 1));
+    const float rinv = 1.f / (sigma + eps);
+    T* yr = y + (long long)row * D;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = (v * 32 + lane) * EV;
+      if (c < D) {
+        float o[EV];
+#pragma unroll
+        for (int i = 0; i < EV; i += 4) {
+          const float4 av = *reinterpret_cast<const float4*>(a + c + i);
+          const float4 bv = *reinterpret_cast<const float4*>(bta + c + i);
+          o[i] = (z[r][v][i] - mean) * rinv * av.x + bv.x;
+          o[i + 1] = (z[r][v][i + 1] - mean) * rinv * av.y + bv.y;
+          o[i + 2] = (z[r][v][i + 2] - mean) * rinv * av.z + bv.z;
+          o[i + 3] = (z[r][v][i + 3] - mean) * rinv * av.w + bv.w;
+        }
+        stv<T, EV>(yr + c, o);
+      }
+    }
+    if (lane == 0) { mean_o[row] = mean; rinv_o[row] = rinv; }
   }
-  if (lane == 0) { mean_o[row] = mean; rinv_o[row] = rinv; }
 }
 
 // backward: dz_i = rinv*(g_i - mean(g)) - c_i * rinv^2 * sum(g*c) / ((D-1)*sigma),  g = dy*a, c = z-mean
@@ -255,16 +266,20 @@ ln_dab_finish_kernel(const float* __restrict__ ws, float* __restrict__ da, float
 template <typename T>
 static int fwd_t(const void* x, const void* res, const float* a, const float* b, void* y, float* mean, float* rinv,
                  int rows, int D, float eps, const pka_dropout& dr, cudaStream_t st) {
-  dim3 grid((rows + kLnWarps - 1) / kLnWarps), block(kLnWarps * 32);
-#define LN_FWD(E, V) launch_k(add_ln_fwd_kernel<T, E, V>, grid, block, 0, st, (const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
+  dim3 block(kLnWarps * 32);
+  // rows per warp: 4 for narrow rows of a large tensor (bytes in flight), 1 otherwise (small tensors want every SM busy)
+#define LN_FWD(E, V, R) launch_k(add_ln_fwd_kernel<T, E, V, R>, dim3((rows + kLnWarps * R - 1) / (kLnWarps * R)), block, 0, st, (const T*)x, (const T*)res, a, b, (T*)y, mean, rinv, rows, D, eps, dr)
+  const bool many = rows >= 16384;
   if (sizeof(T) == 2 && D % 8 == 0 && D > 128) {  // bf16: 8 elements (16 bytes) per lane and vector (D <= 128 would
                                                   // leave half of the warp idle: 4 elements per lane there)
     constexpr int E = sizeof(T) == 2 ? 8 : 4;
     const int vpl = (D + 255) / 256;
-    if (vpl <= 1) LN_FWD(E, 1); else if (vpl <= 2) LN_FWD(E, 2); else LN_FWD(E, 4);
+    if (vpl <= 1) { if (many) LN_FWD(E, 1, 2); else LN_FWD(E, 1, 1); } else if (vpl <= 2) LN_FWD(E, 2, 1); else LN_FWD(E, 4, 1);
   } else {
     const int vpl = (D + 127) / 128;
-    if (vpl <= 1) LN_FWD(4, 1); else if (vpl <= 2) LN_FWD(4, 2); else if (vpl <= 4) LN_FWD(4, 4); else LN_FWD(4, 8);
+    if (vpl <= 1) { if (many) LN_FWD(4, 1, 4); else LN_FWD(4, 1, 1); }
+    else if (vpl <= 2) { if (many) LN_FWD(4, 2, 2); else LN_FWD(4, 2, 1); }
+    else if (vpl <= 4) LN_FWD(4, 4, 1); else LN_FWD(4, 8, 1);
   }
 #undef LN_FWD
   return check_launch("add_layernorm_fwd");
