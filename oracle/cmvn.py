@@ -7,6 +7,11 @@ behaviour for `apply-cmvn --utt2spk=... --norm-vars={false,true}` with per-utter
 src/transform/cmvn.cc, ApplyCmvn): mean is the plain average over the utterance's frames, variance is the *population*
 variance E[x^2]-mean^2 floored at 1e-20, features become (x-mean)[/sqrt(var)].  Padded frames (beyond `length`) stay 0,
 because the reference pads *after* feature extraction (U/instances_handler.py:118-139).
+
+What freezes it (without pinning it against Kaldi): tests/golden/cmvn_hand_computed.json -- known-answer vectors worked
+out by hand from that formula (perfect-square variances, an all-equal feature hitting the 1e-20 floor, N = 1 and N = 0
+utterances, a padding frame), held by tests/test_oracle_vs_golden.py for this file and by tests/test_gpu_ops.py for the
+CUDA front-end.
 """
 from __future__ import annotations
 

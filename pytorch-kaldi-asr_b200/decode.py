@@ -15,7 +15,14 @@ fp32 log-probs; finished hypotheses stay in the beam and compete; no length norm
 only BOS; LayerNormalization is the identity at step 1 (sequence length 1, T/Modules.py:43-44) while the cached K/V of
 position 0 come from a LayerNorm-applied pass (which is what the reference recomputes from step 2 on); ties are broken
 towards the lowest flat candidate index (the reference's np.argsort order for exact ties is unspecified).
-Only bands with end == 0 (causal) can be cached; other bands raise.
+
+Only a causal decoder band (end == 0) can be cached: with end > 0 an earlier position attends to later tokens, so its
+keys/values change whenever the hypothesis grows.  Such bands -- which the reference decodes like any other, because it
+never caches (T/Models.py:38-49, L/decode.py:85) -- take the NO-CACHE path (`BeamDecoder(..., use_cache=False)`,
+chosen automatically): every step re-runs `model.decoder` over the full prefixes of all beam slots through the same
+fp32 kernels as training/evaluation, and the device lattice / top-k kernel advances as in the cached path.  It is
+O(step^2) like the reference and exists for exactness, not speed; `opt.use_cache = False` forces it for a causal band
+(the two paths are tested against each other and against the reference's goldens).
 """
 from __future__ import annotations
 
@@ -35,10 +42,9 @@ class BeamDecoder:
     """Decoding state and step graph for one (n_utt, T, beam, max_len) shape."""
 
     def __init__(self, model, n_utt: int, T: int, beam: int, max_len: int, force_full_length: bool = False,
-                 use_graph: bool = True, poll_every: int = 8):
+                 use_graph: bool = True, poll_every: int = 8, use_cache: bool = True):
         dec = model.decoder
-        if dec.sub[1] != 0:
-            raise RuntimeError("KV-cached decoding needs a causal decoder band (end == 0); got %r" % (dec.sub,))
+        self.cached = bool(use_cache) and int(dec.sub[1]) == 0     # a non-causal band cannot be cached (module docstring)
         if max_len > dec.position_enc.weight.shape[0]:
             raise RuntimeError("max_token_seq_len %d exceeds decoder_max_len %d" % (max_len, dec.position_enc.weight.shape[0]))
         self.model, self.dec = model, dec
@@ -65,9 +71,11 @@ class BeamDecoder:
         self.done = torch.empty(n_utt, **i32)
         self.n_not_done = torch.empty(1, **i32)
         f32 = dict(device=dev, dtype=torch.float32)
-        self.kcache = [torch.empty(n_utt, self.E, self.HD, **f32) for _ in range(self.n_layers)]
-        self.vcache = [torch.empty(n_utt, self.E, self.HD, **f32) for _ in range(self.n_layers)]
-        self.enc_kv = [torch.empty(n_utt, T, 2 * self.HD, **f32) for _ in range(self.n_layers)]
+        n_c = self.n_layers if self.cached else 0                  # the no-cache path keeps none of these
+        self.kcache = [torch.empty(n_utt, self.E, self.HD, **f32) for _ in range(n_c)]
+        self.vcache = [torch.empty(n_utt, self.E, self.HD, **f32) for _ in range(n_c)]
+        self.enc_kv = [torch.empty(n_utt, T, 2 * self.HD, **f32) for _ in range(n_c)]
+        self.enc_rep = self.mask_rep = None                        # no-cache path: encoder memory / mask per beam slot
         self.src_mask = torch.empty(n_utt, T, device=dev, dtype=torch.uint8)
         self.logits = torch.empty(n_utt * beam, self.V, **f32)
         self.desc = L.BeamDesc()
@@ -80,8 +88,8 @@ class BeamDecoder:
         # once into nn.Linear layout [(p,h,j), d], so q|k|v of a step is ONE GEMM instead of three head-batched ones.
         # (re-packed into the same buffers on every reset(), so weight updates between batches are picked up and the
         # captured step graph keeps pointing at valid storage)
-        self.w_qkv = [torch.empty(3 * self.HD, self.D, **f32) for _ in range(self.n_layers)]
-        self.w_q_cross = [torch.empty(self.HD, self.D, **f32) for _ in range(self.n_layers)]
+        self.w_qkv = [torch.empty(3 * self.HD, self.D, **f32) for _ in range(n_c)]
+        self.w_q_cross = [torch.empty(self.HD, self.D, **f32) for _ in range(n_c)]
 
     # ------------------------------------------------------------------------------------------------ state
     def reset(self, enc_output: torch.Tensor, src_pad_mask: torch.Tensor):
@@ -102,6 +110,12 @@ class BeamDecoder:
         self.done.zero_()
         self.n_not_done.fill_(self.n_utt)
         self.src_mask.copy_(src_pad_mask.to(torch.uint8))
+        self.steps_run = 0
+        if not self.cached:
+            # like the reference (L/decode.py:64-75) every beam slot carries its own copy of the encoder memory
+            self.enc_rep = enc_output.to(torch.float32).repeat_interleave(self.beam, 0).contiguous()
+            self.mask_rep = self.src_mask.repeat_interleave(self.beam, 0).contiguous()
+            return
         with torch.no_grad():
             pack = lambda *ws: torch.cat([w.detach().permute(0, 2, 1).reshape(-1, w.shape[1]) for w in ws])
             for l, layer in enumerate(self.dec.layer_stack):
@@ -169,9 +183,48 @@ class BeamDecoder:
         self._decoder_token(skip_ln=False, write_cache=True)
         self._advance()
 
+    # ------------------------------------------------------------------------------------------------ no-cache path
+    def _slot_prefixes(self, length: int) -> torch.Tensor:
+        """Token prefixes int64[n_utt*beam, length] of the beam slots, read off the device lattice along the
+        back-pointers.  Every live hypothesis has exactly `length` tokens; an idle slot points at the BOS edge and gets
+        an all-BOS row (its logits are ignored by `beam_advance`)."""
+        cur = self.slot_edge.long()
+        prev, word = self.edge_prev.long(), self.edge_word.long()
+        toks = torch.full((self.n_utt, self.beam, length), constants.BOS, device=self.dev, dtype=torch.int64)
+        for pos in range(length - 1, -1, -1):
+            alive = cur >= 0
+            safe = cur.clamp(min=0)
+            toks[:, :, pos] = torch.where(alive, word.gather(1, safe), toks[:, :, pos])
+            cur = torch.where(alive, prev.gather(1, safe), cur)
+        return toks.view(self.n_utt * self.beam, length)
+
+    def _run_uncached(self):
+        """The reference's own scheme (L/decode.py:54-98): per step, the whole decoder over the full prefixes.  The
+        decoder call is the model's ordinary forward (fp32 kernels; LayerNormalization is the identity at length 1 by
+        itself, T/Modules.py:43-44); the lattice update stays on the device."""
+        prev_mode = ops.compute_mode()
+        ops.set_compute_mode("fp32")
+        try:
+            steps = 0
+            while steps < self.max_len:
+                tgt = self._slot_prefixes(steps + 1)
+                ones = torch.ones(tgt.shape, device=self.dev, dtype=torch.uint8)      # only the band restricts
+                logits = self.dec(tgt, ones, self.mask_rep, self.enc_rep)[0]            # [n*K, length, V]
+                self.logits.copy_(logits[:, -1, :])
+                self._advance()
+                steps += 1
+                if steps % self.poll_every == 0 and int(self.n_not_done.item()) == 0:
+                    break
+        finally:
+            ops.set_compute_mode(prev_mode)
+        self.steps_run = steps
+        return steps
+
     @torch.no_grad()
     def run(self):
         """Decode until every lattice is done or max_len steps were taken.  Returns the number of steps run."""
+        if not self.cached:
+            return self._run_uncached()
         # step 1: position 0 twice -- LN-applied pass fills the caches of the BOS edge, LN-skipped pass gives the logits
         self._decoder_token(skip_ln=False, write_cache=True)
         self._decoder_token(skip_ln=True, write_cache=False)
@@ -245,7 +298,8 @@ _DECODERS = {}
 def translate_batch(model, batch, opt, model_options=None):
     """Reference signature (L/decode.py:22).  `batch` = (keys, src f32[B,T,F], src_pad_mask u8[B,T], tgt, tgt_mask);
     `opt` carries beam_size, max_token_seq_len, nbest (use_gpu is accepted and ignored: this path is GPU only).
-    Optional extras on `opt`: force_full_length (bool), use_graph (bool)."""
+    Optional extras on `opt`: force_full_length (bool), use_graph (bool), use_cache (bool; False = the reference's
+    no-cache scheme, which is also what a non-causal decoder band gets)."""
     model.eval()
     dev = next(model.parameters()).device
     if dev.type != "cuda":
@@ -259,13 +313,23 @@ def translate_batch(model, batch, opt, model_options=None):
     # the captured step graph holds raw pointers to the decoder weights: the storage fingerprint makes a model whose
     # parameters moved (FusedAdam arena, .to(), dtype change) build a fresh decoder instead of replaying stale addresses
     fingerprint = hash(tuple(p.data_ptr() for p in model.decoder.parameters()))
-    key = (id(model), enc_output.shape[0], enc_output.shape[1], opt.beam_size, opt.max_token_seq_len,
-           bool(getattr(opt, "force_full_length", False)), bool(getattr(opt, "use_graph", True)), fingerprint)
-    bd = _DECODERS.get(key)
-    if bd is None:
-        if len(_DECODERS) > 8:
-            _DECODERS.clear()
-        bd = _DECODERS[key] = BeamDecoder(model, key[1], key[2], key[3], key[4], key[5], key[6])
-    bd.reset(enc_output, fmask)
-    bd.run()
-    return bd.results(opt.nbest)
+    use_cache = bool(getattr(opt, "use_cache", True)) and int(model.decoder.sub[1]) == 0
+    n_utt, T = enc_output.shape[0], enc_output.shape[1]
+    # the no-cache path replicates the encoder memory per beam slot: bound it to ~1 GiB by decoding utterance chunks
+    chunk = n_utt if use_cache else max(1, min(n_utt, (1 << 28) // max(1, opt.beam_size * T * enc_output.shape[2])))
+    hyps, weights = [], []
+    for u0 in range(0, n_utt, chunk):
+        n = min(chunk, n_utt - u0)
+        key = (id(model), n, T, opt.beam_size, opt.max_token_seq_len, bool(getattr(opt, "force_full_length", False)),
+               bool(getattr(opt, "use_graph", True)), fingerprint, use_cache)
+        bd = _DECODERS.get(key)
+        if bd is None:
+            if len(_DECODERS) > 8:
+                _DECODERS.clear()
+            bd = _DECODERS[key] = BeamDecoder(model, n, T, key[3], key[4], key[5], key[6], use_cache=use_cache)
+        bd.reset(enc_output[u0:u0 + n], fmask[u0:u0 + n])
+        bd.run()
+        h, w = bd.results(opt.nbest)
+        hyps += h
+        weights += w
+    return hyps, weights

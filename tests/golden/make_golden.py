@@ -158,8 +158,10 @@ def train_steps_golden(ref, name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
-def decode_golden(ref, name):
-    cfg = dict(SMALL)
+def decode_golden(ref, name, dec_band=(-3, 0)):
+    """`dec_band` with end > 0 is a non-causal decoder band: the reference decodes it like any other (it re-runs the
+    whole decoder over the full prefixes, L/decode.py:81-87); here it pins the no-cache path of decode.py."""
+    cfg = dict(SMALL, decoder_sub_sequence=dec_band)
     model, lda = build(ref, cfg, 5)
     # sharpen the output layer so hypotheses differ clearly and some reach EOS within the step budget
     # and give the encoder more say / make EOS competitive so finished hypotheses stay in the beam and compete
@@ -257,6 +259,7 @@ def main():
     attention_encoder_golden(ref, "attn_encoder_small")
     train_steps_golden(ref, "train_steps_small")
     decode_golden(ref, "decode_small")
+    decode_golden(ref, "decode_small_band1", dec_band=(-3, 1))
     semantics_golden(ref, "semantics")
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

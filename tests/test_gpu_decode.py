@@ -91,10 +91,51 @@ def test_translate_batch_timit_config_vs_oracle(force):
         assert n_steps == max_len and all(len(h[0]) == max_len + 1 for h in hyps)
 
 
-def test_kv_cache_needs_causal_band():
+def _golden_run(name, dec_band, beam, nbest, max_len, **extra):
     import pytorch_kaldi_asr_b200 as pk
     from pytorch_kaldi_asr_b200.decode import translate_batch
-    g = load_golden("decode_small")
-    model = pk.Transformer(lda_mat=g["lda_mat"], **dict(SMALL, decoder_sub_sequence=(-3, 1))).to(DEV)
-    with pytest.raises(RuntimeError):
-        translate_batch(model, (None, g["src"], g["src_mask"], None, None), opt(2, 5, 1), None)
+    g = load_golden(name)
+    model = pk.Transformer(lda_mat=g["lda_mat"], **dict(SMALL, decoder_sub_sequence=dec_band))
+    model.load_state_dict(golden_state_dict(g))
+    model = model.to(DEV)
+    batch = (None, g["src"], g["src_mask"], g["tgt"], None)
+    hyps, weights = translate_batch(model, batch, opt(beam, max_len, nbest, **extra), None)
+    tag = "beam%d." % beam
+    for u in range(len(hyps)):
+        want = [g[tag + "hyp.%d.%d" % (u, j)].tolist() for j in range(int(g[tag + "n_hyp.%d" % u]))]
+        assert hyps[u] == want, (u, hyps[u], want)
+        np.testing.assert_allclose(np.asarray(weights[u]), g[tag + "weights.%d" % u], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("beam,nbest,max_len", [(4, 2, 12), (1, 1, 9)])
+def test_noncausal_decoder_band_vs_reference_golden(beam, nbest, max_len):
+    """Decoder band (-3, 1): not cacheable, decoded by the no-cache path (full-prefix decoder re-runs, like the
+    reference L/decode.py:81-87) -- tokens and scores of the real reference (tests/golden/make_golden.py)."""
+    _golden_run("decode_small_band1", (-3, 1), beam, nbest, max_len)
+
+
+@pytest.mark.parametrize("beam,nbest,max_len", [(4, 2, 12)])
+def test_no_cache_path_on_a_causal_band_matches_the_reference_too(beam, nbest, max_len):
+    """`opt.use_cache = False` forces the no-cache path on the causal band the KV-cached path is tested on above."""
+    _golden_run("decode_small", (-3, 0), beam, nbest, max_len, use_cache=False)
+
+
+def test_no_cache_path_chunks_utterances():
+    """The no-cache path bounds the replicated encoder memory by decoding utterance chunks; chunked == unchunked."""
+    import pytorch_kaldi_asr_b200 as pk
+    from pytorch_kaldi_asr_b200 import decode as D
+    g = load_golden("decode_small_band1")
+    model = pk.Transformer(lda_mat=g["lda_mat"], **dict(SMALL, decoder_sub_sequence=(-3, 1)))
+    model.load_state_dict(golden_state_dict(g))
+    model = model.to(DEV)
+    batch = (None, g["src"], g["src_mask"], g["tgt"], None)
+    whole = D.translate_batch(model, batch, opt(4, 8, 2), None)
+    bd = D.BeamDecoder(model, 2, g["src"].shape[1], 4, 8, use_cache=False)
+    with torch.no_grad():
+        enc, fmask = model.encode(torch.from_numpy(g["src"]).to(DEV), torch.from_numpy(g["src_mask"]).to(DEV))
+    bd.reset(enc[1:3], fmask[1:3])
+    bd.run()
+    part = bd.results(2)
+    assert part[0] == whole[0][1:3]
+    for a, b in zip(part[1], whole[1][1:3]):
+        np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=0, atol=1e-5)

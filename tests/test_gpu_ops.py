@@ -320,6 +320,23 @@ def test_frontend_fold_splice_cmvn(fold, cmvn):
     assert_close(out, ref, 1e-5 if cmvn else 0.0, "frontend")
 
 
+@pytest.mark.parametrize("cmvn", [1, 2])
+def test_frontend_cmvn_vs_hand_computed_vectors(cmvn):
+    """The CMVN of the fused front-end kernel against the hand-computed known-answer vectors
+    (tests/golden/cmvn_hand_computed.json, derivation inside): all-equal feature (variance floor), N = 1, N = 0."""
+    import json
+    import os
+    o = ops()
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cmvn_hand_computed.json")) as fh:
+        g = json.load(fh)
+    x = torch.tensor(g["feats"], dtype=torch.float32)
+    lens = torch.tensor(g["lengths"], dtype=torch.int32)
+    want = torch.tensor(g["mean_var" if cmvn == 2 else "mean_only"], dtype=torch.float32)
+    out = o.frontend(x.to(DEV), lens.to(DEV), 1, [0], cmvn)
+    assert out.shape == want.shape
+    assert (out.cpu() - want).abs().max().item() <= 1e-6
+
+
 def test_concat_layer_known_vector():
     pk = P()
     from pytorch_kaldi_asr_b200.TDNN import ConcatLayer

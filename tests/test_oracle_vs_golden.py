@@ -172,11 +172,14 @@ def test_train_steps_adam_and_lr_schedule():
 
 
 @pytest.mark.parametrize("beam,nbest,max_len", [(4, 2, 12), (1, 1, 9)])
-def test_beam_decode_tokens_and_scores(beam, nbest, max_len):
-    g = load_golden("decode_small")
+@pytest.mark.parametrize("name,dec_band", [("decode_small", (-3, 0)), ("decode_small_band1", (-3, 1))])
+def test_beam_decode_tokens_and_scores(beam, nbest, max_len, name, dec_band):
+    """`decode_small_band1`: a NON-causal decoder band (end = 1), which the reference decodes like any other band
+    because it re-runs the decoder over the full prefixes (L/decode.py:81-87)."""
+    g = load_golden(name)
     sd = golden_state_dict(g)
-    hyps, weights, lats, _ = beam_decode.translate_batch(sd, SMALL, g["src"], g["src_mask"], beam, max_len, nbest,
-                                                         return_lattices=True)
+    hyps, weights, lats, _ = beam_decode.translate_batch(sd, dict(SMALL, decoder_sub_sequence=dec_band), g["src"],
+                                                         g["src_mask"], beam, max_len, nbest, return_lattices=True)
     tag = "beam%d." % beam
     for u in range(len(hyps)):
         assert lats[u].min_gap > 1e-4, "golden input has a near-tie; token parity would be ill-posed"
@@ -202,3 +205,20 @@ def test_philox_restatement_matches_the_published_known_answer_vectors():
     m = philox.keep_mask(200000, 0.35, 3, 1234, 7)
     assert abs(m.mean() - 0.65) < 5e-3
     assert philox.keep_mask(10, 0.0, 1, 2, 3).all()
+
+
+@pytest.mark.parametrize("norm_vars", [False, True])
+def test_cmvn_restatement_vs_hand_computed_vectors(norm_vars):
+    """oracle/cmvn.py against tests/golden/cmvn_hand_computed.json: values worked out by hand from the formula Kaldi
+    documents for apply-cmvn (the derivation is in the fixture).  Freezes the arithmetic (mean over real frames only,
+    population variance, 1e-20 floor, padding stays zero, N = 1 and N = 0 utterances); no Kaldi binary is involved."""
+    import json
+    import os
+    from oracle import cmvn
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cmvn_hand_computed.json")) as fh:
+        g = json.load(fh)
+    x = np.asarray(g["feats"], dtype=np.float32)
+    got = cmvn.apply_cmvn(x, np.asarray(g["lengths"]), norm_vars=norm_vars)
+    want = np.asarray(g["mean_var" if norm_vars else "mean_only"], dtype=np.float64)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
