@@ -278,13 +278,14 @@ def roofline_probe(model, B, T, pk, mode):
 
 def hbm_probe():
     """The residual-add + LayerNorm forward kernel THE TIMED STEP RUNS (bf16 activation stream, D = 128:
-    add_ln_fwd_kernel<__nv_bfloat16, 4, 1, R>, R = rows per warp), at the step's own shape (B*L = 2016 rows of 128: 1.5 MB, latency-bound) and
+    add_ln_fwd_kernel<__nv_bfloat16, 8, 16, 1, DROP>: 16-byte vectors, 16 lanes per row = two rows per warp iteration,
+    persistent grid with the gain / offset in registers), at the step's own shape (B*L = 2016 rows of 128: 1.5 MB, latency-bound) and
     at a bandwidth-sized shape (> L2), CUDA-graph-timed alone.  Algorithmic bytes = 3 * rows * D * 2 (read x, read
     residual, write y)."""
     from pytorch_kaldi_asr_b200 import ops
     pk_ = peaks()
-    out = {"kernel": "add_ln_fwd_kernel<__nv_bfloat16, 4, 1, R> (dropout(x) + residual -> LayerNormalization, bf16 in/out; "
-                     "R = 1 row per warp at the in-step shape, 4 at the bandwidth-sized one)",
+    out = {"kernel": "add_ln_fwd_kernel<__nv_bfloat16, 8, 16, 1, false> (dropout(x) + residual -> LayerNormalization, bf16 in/out; "
+                     "16 lanes x 16 bytes per 128-wide row, persistent grid, next rows prefetched)",
            "bound": "hbm", "peak": pk_["hbm_gbs"], "unit": "GB/s", "peak_source": pk_["source"] + " copy bandwidth"}
     for name, rows, D, nbuf in (("in_step", 2016, 128, 64), ("bandwidth_sized", 32 * 430 * 64, 128, 2)):
         xs = [torch.randn(rows, D, device="cuda").bfloat16() for _ in range(nbuf)]      # in-step: 64 x 0.5 MB rotate
@@ -472,7 +473,8 @@ def decode_bench(model, pk, rank, world, n_total=1000, batch=125, beam=10, max_l
 
 def decode_roofline_probe(n_utt=125, T=499, beam=10, H=2, dk=64):
     """Dominant HBM stream of a beam-search step: cross-attention of the `beam` live hypotheses of every utterance over
-    its T encoder frames (attn_fwd_smallq_kernel, fp32 exact path).  Algorithmic bytes per launch = the K/V rows read
+    its T encoder frames (attn_fwd_smallq_split_kernel: a cluster of 4 CTAs per (utterance, head), one slice of <= 128 keys
+    each, fp32 exact path; every key is live in this probe).  Algorithmic bytes per launch = the K/V rows read
     once per utterance, n_utt * T * (dk + dv) * H * 4; 3 launches per step (one per decoder layer)."""
     from pytorch_kaldi_asr_b200 import ops
     HD = H * dk
@@ -490,7 +492,8 @@ def decode_roofline_probe(n_utt=125, T=499, beam=10, H=2, dk=64):
     sec = time_kernel(f, iters=8, replays=3)
     nbytes = float(n_utt) * T * 2 * HD * 4
     pk_ = peaks()
-    return {"kernel": "attn_fwd_smallq_kernel (beam = query axis, K/V shared per utterance, fp32)", "bound": "hbm",
+    return {"kernel": "attn_fwd_smallq_split_kernel<12> (beam = query axis, K/V shared per utterance, key-split cluster of 4, "
+                      "bulk-copied slices, DSMEM combine, fp32)", "bound": "hbm",
             "n_utt": n_utt, "T": T, "beam": beam, "bytes_per_launch": nbytes, "us_per_launch": sec * 1e6,
             "achieved": nbytes / sec / 1e9, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / pk_["hbm_gbs"],
             "peak_source": pk_["source"] + " copy bandwidth"}

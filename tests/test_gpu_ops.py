@@ -195,6 +195,41 @@ def test_attention_fwd_bwd(B, H, Lq, Lk, D, band, selfattn, p):
         assert_close(kvg.grad, kvr.grad, 1e-3, "attn dkv")
 
 
+@pytest.mark.parametrize("onepass", [False, True])
+@pytest.mark.parametrize("B,H,Lq,Lk", [(3, 2, 10, 499), (2, 2, 3, 64), (3, 1, 16, 131), (2, 3, 7, 700), (2, 2, 12, 1024),
+                                       (2, 2, 5, 1100)])
+def test_attention_few_queries_many_keys(B, H, Lq, Lk, onepass, monkeypatch):
+    """The beam-search cross-attention shape (<= 16 queries, head width 64, no band): the key-split cluster kernel
+    (slices of <= 128 keys, bulk copies, distributed-shared-memory combine; up to 1024 keys) and the one-pass kernel
+    behind it (PKA_SMALLQ_ONEPASS=1, and beyond 1024 keys) against dense attention.  Masks with holes, an utterance
+    whose keys are all masked (output 0, no NaN), a slice with no live key at all."""
+    o = ops()
+    if onepass:
+        monkeypatch.setenv("PKA_SMALLQ_ONEPASS", "1")
+    D, HD = 64, H * 64
+    scale = 1.0 / math.sqrt(128.0)
+    g = torch.Generator().manual_seed(Lk)
+    key_mask = (torch.rand(B, Lk, generator=g) > 0.3).to(torch.uint8)
+    key_mask[0, Lk // 3:] = 0                                  # prefix mask: the later slices hold no live key
+    key_mask[0, :2] = 1
+    if B > 2:
+        key_mask[2] = 0                                        # dead utterance
+    qbuf, kvbuf = rnd(B, Lq, HD, seed=1), rnd(B, Lk, 2 * HD, seed=2)
+    if not onepass and Lk <= 1024:
+        kvbuf[key_mask == 0] = float("nan")                    # the split kernel never fetches a masked row
+    qr = qbuf.clone().requires_grad_(True)
+    kv_clean = torch.nan_to_num(kvbuf, nan=0.0)
+    q_ = qr.reshape(B, Lq, H, D).permute(0, 2, 1, 3)
+    k_, v_ = [t.reshape(B, Lk, H, D).permute(0, 2, 1, 3) for t in kv_clean.split(HD, dim=-1)]
+    ref, _ = dense_attention(q_, k_, v_, key_mask, None, scale, None, 0.0)
+    ref = torch.nan_to_num(ref, nan=0.0)                       # dense softmax of an all-masked row is NaN; ours is 0
+    out, _ = o.attention(qbuf.to(DEV), kvbuf.to(DEV), key_mask.to(DEV), H, D, None, scale, None)
+    assert torch.isfinite(out).all()
+    assert_close(out, ref, 1e-4, "few-query attention")
+    if B > 2:
+        assert float(out[2].abs().max()) == 0.0
+
+
 def test_attention_fully_masked_rows_are_zero_not_nan():
     o = ops()
     B, H, L, D = 2, 2, 12, 64
@@ -209,7 +244,11 @@ def test_attention_fully_masked_rows_are_zero_not_nan():
 
 
 # ------------------------------------------------------------------------------------------------ add + LayerNorm
-@pytest.mark.parametrize("rows,D,p", [(40, 32, 0.0), (1760, 128, 0.0), (300, 256, 0.35), (77, 512, 0.35)])
+# (lane-group geometries of csrc/layernorm.cu: 8 / 16 / 32 lanes per row, 1-4 vectors per lane, widths that do not fill the
+# group, row counts that leave a warp's last rows empty; the last two walk several rows per warp behind the prefetch with
+# 296 and 888 partial rows)
+@pytest.mark.parametrize("rows,D,p", [(40, 32, 0.0), (1760, 128, 0.0), (300, 256, 0.35), (76, 512, 0.35), (44, 40, 0.35),
+                                      (52, 200, 0.0), (36, 64, 0.35), (10004, 128, 0.35), (30000, 64, 0.0)])
 def test_add_layernorm_fwd_bwd(rows, D, p):
     o = ops()
     x, r = rnd(4, rows // 4, D, seed=1), rnd(4, rows // 4, D, seed=2)
@@ -231,6 +270,37 @@ def test_add_layernorm_fwd_bwd(rows, D, p):
     assert_close(rg.grad, rr.grad, 1e-3, "ln dres")
     assert_close(ag.grad, ar.grad, 1e-3, "ln da")
     assert_close(bg.grad, br.grad, 1e-3, "ln db")
+
+
+@pytest.mark.parametrize("rows,D,p", [(2016, 128, 0.35), (300, 256, 0.0), (52, 512, 0.1), (44, 64, 0.0), (36, 200, 0.35),
+                                      (36, 204, 0.0), (12792, 512, 0.1), (40000, 256, 0.0)])
+def test_add_layernorm_bf16_fwd_bwd(rows, D, p):
+    """The bf16 instantiations (16-byte vectors of 8, 8-byte vectors of 4 for D % 8 != 0) against fp32 math on the same
+    bf16-rounded inputs: outputs and data gradients within bf16 rounding (1e-2 of the tensor scale), the fp32 gain /
+    offset gradients 2e-3."""
+    o = ops()
+    bf = lambda t: t.bfloat16().float()
+    x, r = bf(rnd(4, rows // 4, D, seed=1)), bf(rnd(4, rows // 4, D, seed=2))
+    a, b = rnd(D, seed=3) * 0.5 + 1.0, rnd(D, seed=4) * 0.1
+    gy = bf(rnd(4, rows // 4, D, seed=5))
+    keep, drop = None, None
+    if p > 0:
+        drop = o.Drop(p, 11, 5, torch.tensor([2], dtype=torch.int64, device=DEV))
+        keep = o.dropout_keep_mask(x.numel(), drop, DEV).cpu().view(x.shape).float()
+    xr, rr, ar, br = [t.clone().requires_grad_(True) for t in (x, r, a, b)]
+    z = (xr if keep is None else xr * keep / (1 - p)) + rr
+    ref = am.layer_norm_ref(z, ar, br)
+    ref.backward(gy)
+    xg, rg = [t.clone().to(DEV).bfloat16().requires_grad_(True) for t in (x, r)]
+    ag, bg = [t.clone().to(DEV).requires_grad_(True) for t in (a, b)]
+    out = o.add_layer_norm(xg, rg, ag, bg, 1e-3, drop)
+    assert out.dtype == torch.bfloat16
+    out.backward(gy.to(DEV).bfloat16())
+    assert_close(out.float(), ref, 1e-2, "ln bf16 fwd")
+    assert_close(xg.grad.float(), xr.grad, 1e-2, "ln bf16 dx")
+    assert_close(rg.grad.float(), rr.grad, 1e-2, "ln bf16 dres")
+    assert_close(ag.grad, ar.grad, 2e-3, "ln bf16 da")
+    assert_close(bg.grad, br.grad, 2e-3, "ln bf16 db")
 
 
 # ------------------------------------------------------------------------------------------------ loss
@@ -304,20 +374,27 @@ def test_dropout_mask_depends_on_step_and_site_and_rate():
 
 # ------------------------------------------------------------------------------------------------ front-end
 @pytest.mark.parametrize("fold,cmvn", [(1, 0), (2, 0), (1, 1), (3, 2)])
-def test_frontend_fold_splice_cmvn(fold, cmvn):
+@pytest.mark.parametrize("T,Fd,ctx", [(37, 40, [-2, -1, 0, 1, 2]), (150, 40, [-2, -1, 0, 1, 2]), (203, 24, [-3, 0, 4]),
+                                      (131, 6, [0]), (90, 40, [1, 2])])
+def test_frontend_fold_splice_cmvn(fold, cmvn, T, Fd, ctx):
+    """T > 64 spans several shared-memory tiles of the tile kernel (halo frames across tile edges, a last partial tile);
+    F = 6 takes the direct kernel (no 16-byte vectors); one-sided and asymmetric contexts."""
     o = ops()
-    B, T, Fd = 4, 37, 40
-    lens = np.array([37, 20, 31, 5])
+    B = 4
+    lens = np.array([T, T // 2 + 1, T - 6, 5])
     x = rnd(B, T, Fd, seed=1).numpy() * 2 + 0.5
     for b, n in enumerate(lens):
         x[b, n:] = 0
     ref = torch.from_numpy(ocmvn.apply_cmvn(x, lens, norm_vars=(cmvn == 2)) if cmvn else x)
     mask = torch.from_numpy((np.arange(T)[None] < lens[:, None]).astype(np.uint8))
     ref, _ = am.fold_frames(ref, mask, fold)
-    ref = am.splice(ref, [-2, -1, 0, 1, 2])
-    out = o.frontend(torch.from_numpy(x).to(DEV), torch.from_numpy(lens).to(DEV), fold, [-2, -1, 0, 1, 2], cmvn)
+    ref = am.splice(ref, ctx)
+    out = o.frontend(torch.from_numpy(x).to(DEV), torch.from_numpy(lens).to(DEV), fold, ctx, cmvn)
     assert out.shape == ref.shape
     assert_close(out, ref, 1e-5 if cmvn else 0.0, "frontend")
+    out16 = o.frontend(torch.from_numpy(x).to(DEV), torch.from_numpy(lens).to(DEV), fold, ctx, cmvn, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16 and out16.shape == ref.shape
+    assert torch.equal(out16, out.bfloat16()), "frontend bf16: not the fp32 result rounded once"
 
 
 @pytest.mark.parametrize("cmvn", [1, 2])
