@@ -473,8 +473,7 @@ def decode_bench(model, pk, rank, world, n_total=1000, batch=125, beam=10, max_l
 
 def decode_roofline_probe(n_utt=125, T=499, beam=10, H=2, dk=64):
     """Dominant HBM stream of a beam-search step: cross-attention of the `beam` live hypotheses of every utterance over
-    its T encoder frames (attn_fwd_smallq_split_kernel: a cluster of 4 CTAs per (utterance, head), one slice of <= 128 keys
-    each, fp32 exact path; every key is live in this probe).  Algorithmic bytes per launch = the K/V rows read
+    its T encoder frames (attn_fwd_smallq_kernel, fp32 exact path).  Algorithmic bytes per launch = the K/V rows read
     once per utterance, n_utt * T * (dk + dv) * H * 4; 3 launches per step (one per decoder layer)."""
     from pytorch_kaldi_asr_b200 import ops
     HD = H * dk
@@ -492,8 +491,7 @@ def decode_roofline_probe(n_utt=125, T=499, beam=10, H=2, dk=64):
     sec = time_kernel(f, iters=8, replays=3)
     nbytes = float(n_utt) * T * 2 * HD * 4
     pk_ = peaks()
-    return {"kernel": "attn_fwd_smallq_split_kernel<12> (beam = query axis, K/V shared per utterance, key-split cluster of 4, "
-                      "bulk-copied slices, DSMEM combine, fp32)", "bound": "hbm",
+    return {"kernel": "attn_fwd_smallq_kernel (beam = query axis, K/V shared per utterance, fp32)", "bound": "hbm",
             "n_utt": n_utt, "T": T, "beam": beam, "bytes_per_launch": nbytes, "us_per_launch": sec * 1e6,
             "achieved": nbytes / sec / 1e9, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / pk_["hbm_gbs"],
             "peak_source": pk_["source"] + " copy bandwidth"}

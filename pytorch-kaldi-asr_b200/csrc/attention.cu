@@ -12,9 +12,8 @@
 //
 // Work split: one warp owns one "row item" (a query in fwd/dq, a key in dk/dv) and streams 32-wide tiles of the
 // other axis through shared memory, lane = item inside the tile; reductions over the tile use warp shuffles.
-#include "tc_common.cuh"
+#include "common.cuh"
 #include <math_constants.h>
-#include <stdlib.h>
 
 namespace pka {
 
@@ -310,6 +309,12 @@ attn_bwd_dkv_kernel(const AttnP p, const T* __restrict__ q, const T* __restrict_
 //   phase 2  warp = query: max / sum over the keys, probabilities normalised in place
 //   phase 3  lane = two output columns: out[q][:] += P[q][j] * V[j][:] with coalesced V rows, 8 warps interleave the keys
 // fp32 throughout; rows without an allowed key give 0 / -inf like the generic kernel.
+// Tried and removed (round 2): a key-split variant -- a cluster of 4 CTAs per (utterance, head), every live K / V row of
+// a 128-key slice requested up front as a 256-byte bulk copy, partial results combined through distributed shared
+// memory.  Correct, but SLOWER (46 vs 41 us at 125 utterances x 499 keys, 83 vs 62 us at 250): each of the 2000 short
+// CTAs pays the mask -> expect_tx -> copy -> cluster-barrier -> remote-read latency chain for only 64 KB of traffic.
+// The ceiling is not the copy bandwidth either: 12 fp32 queries per key are 6 FLOP per K/V byte, i.e. ~40 TFLOP/s of
+// SIMT FMAs at HBM speed (more than half of the fp32 peak before a single shared-memory load is counted).
 constexpr int kSqMaxQ = 16;
 // NQ = queries rounded up to a multiple of 4 (beam 10 -> 12): the score / output loops are fully unrolled over NQ, so a
 // 16-wide instantiation would spend a quarter of its FMAs on padding
@@ -456,210 +461,6 @@ static int fill(AttnP& p, const pka_attn_desc* d, const char* who) {
   return PKA_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ few queries, key-split
-// The same job (<= 16 queries against all encoder frames of one (utterance, head)) as a thread-block CLUSTER along the
-// keys: the S CTAs of a cluster (S = 1, 2, 4, 8) each own a slice of <= 128 keys, and
-//   * every live key / value row of the slice is requested at kernel start as its own 256-byte bulk copy
-//     (cp.async.bulk global -> shared, mbarrier complete_tx): the whole slice (up to 64 KB per CTA) is in flight at once
-//     with no register cost, masked (padding) rows are not fetched at all;
-//   * scores / softmax / P.V run out of shared memory per slice (unnormalised exp against the slice maximum);
-//   * the slices meet through distributed shared memory: rank 0 reads the S partial outputs with their (max, sum)
-//     and writes the normalised result -- no workspace, no second launch.
-// Measured before (round 2, ncu, 250 utterances x 2 heads x 499 keys): attn_fwd_smallq_kernel 62 us = 27 % of the copy
-// bandwidth; one CTA per (utterance, head) left ~16 KB in flight per CTA in the P.V pass and 250 CTAs on 296 slots.
-__device__ __forceinline__ uint32_t sq_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t sq_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void sq_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float sq_ld_remote(const float* local, uint32_t rank) {
-  uint32_t ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sq_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-constexpr int kSqRows = 128;                       // keys per slice
-constexpr int kSqRS = 68;                          // padded shared-memory row stride in floats (272 B: LDS.128 of
-                                                   // consecutive rows fall in different banks, copies stay 16-byte aligned)
-template <int NQ> constexpr int sq_split_smem() {
-  return (2 * kSqRows * kSqRS + NQ * kSqRows + 2 * NQ * 64 + 2 * NQ) * (int)sizeof(float) + 16;
-}
-template <int NQ>
-__global__ void __launch_bounds__(256, 2)
-attn_fwd_smallq_split_kernel(const AttnP p, const float* __restrict__ q, const float* __restrict__ k,
-                             const float* __restrict__ v, const uint8_t* __restrict__ kmask, float* __restrict__ out,
-                             float* __restrict__ lse, int R) {
-  constexpr int D = 64, NQH = NQ / 2;
-  extern __shared__ __align__(16) float sm[];
-  float* Ks = sm;                                  // [128][RS]; later the cross-warp reduction buffer red[8][NQ][D]
-  float* Vs = Ks + kSqRows * kSqRS;                // [128][RS]
-  float* S = Vs + kSqRows * kSqRS;                 // [NQ][128] scores -> exp(score - slice max)
-  float* Qs = S + NQ * kSqRows;                    // [NQ][D]
-  float* part = Qs + NQ * D;                       // [NQ][D] unnormalised output of this slice
-  float* ml = part + NQ * D;                       // [2][NQ] slice max | slice sum
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ml + 2 * NQ);
-  float* red = Ks;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const uint32_t rank = sq_cluster_rank(), csize = sq_cluster_size();
-  const uint32_t barK = smem_u32(&bars[0]), barV = smem_u32(&bars[1]);
-  if (tid == 0) {
-    mbar_init(barK, 1);
-    mbar_init(barV, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_wait();
-  const int j0 = (int)rank * R;
-  int nrows = p.Lk - j0;
-  nrows = nrows < 0 ? 0 : (nrows > R ? R : nrows);
-  const int r = tid & (kSqRows - 1), half = tid >> 7;          // two threads per key row
-  const int j = j0 + r;
-  const bool ok = r < nrows && kmask[(long long)b * p.Lk + j] != 0;
-  const int n_live = __syncthreads_count(ok && half == 0);
-  if (tid == 0) {
-    if (n_live > 0) { mbar_expect_tx(barK, (uint32_t)n_live * 256u); mbar_expect_tx(barV, (uint32_t)n_live * 256u); }
-    else { mbar_arrive(barK); mbar_arrive(barV); }
-  }
-  __syncthreads();
-  if (ok) {
-    if (half == 0) sq_bulk_g2s(smem_u32(Ks + r * kSqRS), k + ((long long)b * p.Lk + j) * p.ldk + h * D, 256u, barK);
-    else sq_bulk_g2s(smem_u32(Vs + r * kSqRS), v + ((long long)b * p.Lk + j) * p.ldv + h * D, 256u, barV);
-  } else if (half == 1) {                          // a masked value row meets probability 0: it must not hold NaN bits
-#pragma unroll
-    for (int d4 = 0; d4 < D / 4; ++d4) *reinterpret_cast<float4*>(Vs + r * kSqRS + d4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int e = tid; e < NQ * D; e += 256) {
-    const int qi = e >> 6, d = e & 63;
-    Qs[e] = qi < p.Lq ? q[((long long)b * p.Lq + qi) * p.ldq + h * D + d] : 0.f;
-  }
-  __syncthreads();
-  // ---- phase 1: scores of this thread's key row against its half of the queries
-  mbar_wait(barK, 0);
-  {
-    float s[NQH];
-#pragma unroll
-    for (int i = 0; i < NQH; ++i) s[i] = 0.f;
-    if (ok) {
-      const float* kr = Ks + r * kSqRS;
-      const float* qb = Qs + half * NQH * D;
-#pragma unroll
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 kv = *reinterpret_cast<const float4*>(kr + d4 * 4);
-#pragma unroll
-        for (int i = 0; i < NQH; ++i) {
-          const float4 qv = *reinterpret_cast<const float4*>(qb + i * D + d4 * 4);
-          s[i] = fmaf(qv.x, kv.x, s[i]); s[i] = fmaf(qv.y, kv.y, s[i]);
-          s[i] = fmaf(qv.z, kv.z, s[i]); s[i] = fmaf(qv.w, kv.w, s[i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NQH; ++i) S[(half * NQH + i) * kSqRows + r] = ok ? s[i] * p.scale : -CUDART_INF_F;
-  }
-  __syncthreads();
-  // ---- phase 2: slice maximum / sum per query, probabilities left unnormalised
-  for (int qi = warp; qi < NQ; qi += 8) {
-    float4 sv = *reinterpret_cast<const float4*>(S + qi * kSqRows + lane * 4);
-    const float m = warp_max(fmaxf(fmaxf(sv.x, sv.y), fmaxf(sv.z, sv.w)));
-    float l = 0.f;
-    if (m != -CUDART_INF_F) {
-      sv.x = __expf(sv.x - m); sv.y = __expf(sv.y - m); sv.z = __expf(sv.z - m); sv.w = __expf(sv.w - m);
-      l = (sv.x + sv.y) + (sv.z + sv.w);
-    } else {
-      sv = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    l = warp_sum(l);
-    *reinterpret_cast<float4*>(S + qi * kSqRows + lane * 4) = sv;
-    if (lane == 0) { ml[qi] = m; ml[NQ + qi] = l; }
-  }
-  __syncthreads();
-  // ---- phase 3: partial out = P V, a warp per key row (8 interleaved), a lane per two output columns
-  mbar_wait(barV, 0);
-  {
-    float acc[NQ][2];
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) { acc[qi][0] = 0.f; acc[qi][1] = 0.f; }
-#pragma unroll 2
-    for (int jj = warp; jj < nrows; jj += 8) {
-      const float2 vv = *reinterpret_cast<const float2*>(Vs + jj * kSqRS + lane * 2);
-#pragma unroll
-      for (int qi = 0; qi < NQ; ++qi) {
-        const float pj = S[qi * kSqRows + jj];
-        acc[qi][0] = fmaf(pj, vv.x, acc[qi][0]);
-        acc[qi][1] = fmaf(pj, vv.y, acc[qi][1]);
-      }
-    }
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi)                // (Ks is dead since the barrier after phase 1: red aliases it)
-      *reinterpret_cast<float2*>(red + (warp * NQ + qi) * D + lane * 2) = make_float2(acc[qi][0], acc[qi][1]);
-  }
-  __syncthreads();
-  for (int e = tid; e < NQ * D; e += 256) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w * NQ * D + e];
-    part[e] = t;
-  }
-  // ---- the slices meet: rank 0 reads every CTA's (max, sum, partial output) through distributed shared memory
-  sq_cluster_sync();
-  if (rank == 0) {
-    for (int e = tid; e < p.Lq * D; e += 256) {
-      const int qi = e >> 6, d = e & 63;
-      float mr[8], M = -CUDART_INF_F;
-#pragma unroll
-      for (uint32_t c = 0; c < 8; ++c) {
-        mr[c] = c < csize ? sq_ld_remote(ml + qi, c) : -CUDART_INF_F;
-        M = fmaxf(M, mr[c]);
-      }
-      float Lt = 0.f, o = 0.f;
-#pragma unroll
-      for (uint32_t c = 0; c < 8; ++c) {
-        if (c < csize && mr[c] != -CUDART_INF_F) {
-          const float w = __expf(mr[c] - M);
-          Lt = fmaf(w, sq_ld_remote(ml + NQ + qi, c), Lt);
-          o = fmaf(w, sq_ld_remote(part + e, c), o);
-        }
-      }
-      out[((long long)b * p.Lq + qi) * p.ldo + h * D + d] = Lt > 0.f ? o / Lt : 0.f;
-      if (d == 0) lse[((long long)b * p.H + h) * p.Lq + qi] = Lt > 0.f ? M + __logf(Lt) : -CUDART_INF_F;
-    }
-  }
-  sq_cluster_sync();                               // nobody's shared memory goes away while rank 0 still reads it
-}
-
-template <int NQ>
-static int launch_smallq_split(const AttnP& p, const float* q, const float* k, const float* v, const uint8_t* km, float* out,
-                               float* lse, int S, int R, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_smallq_split_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, sq_split_smem<NQ>());
-    PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_fwd: cannot opt in to shared memory: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.H, p.B, S);
-  cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = sq_split_smem<NQ>();
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_smallq_split_kernel<NQ>, p, q, k, v, km, out, lse, R);
-  PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_fwd(smallq split) launch failed: %s", cudaGetErrorString(e));
-  return check_launch("attn_fwd(smallq split)");
-}
-
 #define PKA_ATT_DISPATCH(D_, CALL)                 \
   switch (D_) {                                    \
     case 16: { constexpr int DD = 16; CALL; } break;   \
@@ -682,18 +483,6 @@ template <typename T>
 static int fwd_t(const AttnP& p, int D, const void* q, const void* k, const void* v, const uint8_t* km, void* out,
                  float* lse, float* probs, cudaStream_t st) {
   int LkP = 0, smem = 0;
-  if (sizeof(T) == 4 && !probs && smallq_ok(p, D, q, k, v, &LkP, &smem) && p.Lk <= 8 * kSqRows && p.B <= 65535 &&
-      (p.ldk * 4) % 16 == 0 && (p.ldv * 4) % 16 == 0 && !getenv("PKA_SMALLQ_ONEPASS")) {
-    // key-split cluster kernel: the smallest power-of-two number of slices with <= 128 keys each
-    int S = 1;
-    while (S * kSqRows < p.Lk) S <<= 1;
-    const int R = (p.Lk + S - 1) / S;
-    const float *qf = (const float*)q, *kf = (const float*)k, *vf = (const float*)v;
-    if (p.Lq <= 4) return launch_smallq_split<4>(p, qf, kf, vf, km, (float*)out, lse, S, R, st);
-    if (p.Lq <= 8) return launch_smallq_split<8>(p, qf, kf, vf, km, (float*)out, lse, S, R, st);
-    if (p.Lq <= 12) return launch_smallq_split<12>(p, qf, kf, vf, km, (float*)out, lse, S, R, st);
-    return launch_smallq_split<16>(p, qf, kf, vf, km, (float*)out, lse, S, R, st);
-  }
   if (sizeof(T) == 4 && !probs && smallq_ok(p, D, q, k, v, &LkP, &smem)) {
     static bool smem_set = false;
     if (!smem_set) {

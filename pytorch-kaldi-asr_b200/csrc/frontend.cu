@@ -35,24 +35,14 @@ cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths, 
         q[0] += (double)v.x * v.x; q[1] += (double)v.y * v.y; q[2] += (double)v.z * v.z; q[3] += (double)v.w * v.w;
       };
       const float4* x4 = reinterpret_cast<const float4*>(xb);
-      // software pipeline: the four loads of round r+1 are requested before the (double-precision) accumulation of round r,
-      // so a thread always has 4-8 vectors in flight (the plain 4x-unrolled loop issued, waited and accumulated in turn:
-      // 73 % of the issue slots had no eligible warp, 61 % of the copy bandwidth at a bandwidth-sized batch)
-      const long long step = 4LL * nact;
       long long e = tid;
-      float4 c0, c1, c2, c3;
-      bool have = e + 3LL * nact < n4;
-      if (have) { c0 = x4[e]; c1 = x4[e + nact]; c2 = x4[e + 2LL * nact]; c3 = x4[e + 3LL * nact]; }
-      while (have) {
-        const long long en = e + step;
-        const bool more = en + 3LL * nact < n4;
-        float4 d0, d1, d2, d3;
-        if (more) { d0 = x4[en]; d1 = x4[en + nact]; d2 = x4[en + 2LL * nact]; d3 = x4[en + 3LL * nact]; }
-        acc(c0); acc(c1); acc(c2); acc(c3);
-        e = en;
-        have = more;
-        if (more) { c0 = d0; c1 = d1; c2 = d2; c3 = d3; }
+      for (; e + 3LL * nact < n4; e += 4LL * nact) {           // four independent loads in flight per thread
+        const float4 v0 = x4[e], v1 = x4[e + nact], v2 = x4[e + 2LL * nact], v3 = x4[e + 3LL * nact];
+        acc(v0); acc(v1); acc(v2); acc(v3);
       }
+      // (round 2: a software-pipelined version with the next four loads requested before the accumulation needed 70
+      //  registers = 3 CTAs per SM and was slower, 55 % vs 61 % of the copy bandwidth at 2048 utterances: the limit is the
+      //  serial part of every short CTA -- length load, then the fixed-order finish below -- and the 3.5-wave tail)
       for (; e < n4; e += nact) acc(x4[e]);
     } else {
       for (long long e = tid; e < (long long)n * F; e += nact) { const double v = xb[e]; s[0] += v; q[0] += v * v; }
@@ -158,6 +148,10 @@ frontend_kernel(const FrontP p, const float* __restrict__ x, const int* __restri
 //      loads, CMVN applied once per input element (mean / inverse deviation from shared memory), zeros outside [0, T);
 //   2. emit: a warp per output frame, a lane per VEC-wide column group; the column -> (context, frame in the fold,
 //      feature) split is done once per lane, an item is two LDS.128 + one 16-byte store, no division, no global re-read.
+//      The tile is stored in 16-byte units with unit u at u ^ ((u >> 3) & 1): a lane that reads units 2g and 2g+1 (its 8
+//      floats) would otherwise make every LDS.128 of a warp hit only the even (or odd) units of each 128-byte bank row
+//      (2-way conflicts, L1/TEX was the busiest unit at 71 %); with the swap in every other bank row the 8 lanes of a
+//      quarter warp touch 8 different units.
 // Before (round 2, ncu, 2048 x 499 x 40 -> 200 bf16 columns): 111 warp instructions per item (64-bit divisions) and five
 // L1 reads of every input element, the CMVN arithmetic repeated per copy: 66 % of the copy bandwidth without, 41 % with CMVN.
 template <typename To, int VEC>
@@ -165,14 +159,14 @@ __global__ void __launch_bounds__(256)
 frontend_tile_kernel(const FrontP p, int TT, int tiles, int smin, int smax, const float* __restrict__ x,
                      const int* __restrict__ lengths, const float* __restrict__ stats, To* __restrict__ out) {
   pdl_wait();
-  extern __shared__ __align__(16) float fe_sm[];
+  extern __shared__ __align__(128) float fe_sm[];
   const int F = p.F, fold = p.fold, Tf = p.T / fold, Ff = F * fold, W = p.n_ctx * Ff, G = W / VEC;
   const int b = blockIdx.x / tiles, t0 = (blockIdx.x - b * tiles) * TT;
   const int t1 = t0 + TT < Tf ? t0 + TT : Tf;
   const int f_lo = (t0 + smin) * fold;             // first staged input frame (may be negative: zero fill)
   const int n_fr = (TT + smax - smin) * fold;
   float* st = fe_sm;                               // [mean | 1/sigma][F]   (CMVN only)
-  float* tile = fe_sm + (p.cmvn ? 2 * F : 0);      // [n_fr][F]
+  float* tile = fe_sm + (p.cmvn ? (2 * F + 31) / 32 * 32 : 0);      // [n_fr][F] in swizzled 16-byte units, 128-byte aligned
   const int tid = threadIdx.x;
   int len = p.T;
   if (p.cmvn) {
@@ -200,7 +194,8 @@ frontend_tile_kernel(const FrontP p, int TT, int tiles, int smin, int smax, cons
           }
         }
       }
-      *reinterpret_cast<float4*>(tile + fr * F + f4 * 4) = v;
+      const int u = fr * F4 + f4;
+      reinterpret_cast<float4*>(tile)[u ^ ((u >> 3) & 1)] = v;
       fr += dfr; f4 += df4;
       if (f4 >= F4) { f4 -= F4; ++fr; }
     }
@@ -210,7 +205,8 @@ frontend_tile_kernel(const FrontP p, int TT, int tiles, int smin, int smax, cons
   for (int g = lane; g < G; g += 32) {
     const int col = g * VEC, c = col / Ff, fp = col - c * Ff, frr = fp / F, f = fp - frr * F;
     const int shift = p.ctx[c];
-    const float* src0 = tile + (frr - f_lo) * F + f;
+    const int u0 = ((frr - f_lo) * F + f) >> 2;   // first 16-byte unit of this lane's columns in tile row ts = 0
+    const float4* tile4 = reinterpret_cast<const float4*>(tile);
 #pragma unroll 4
     for (int t = t0 + warp; t < t1; t += 8) {
       const int ts = t + shift;
@@ -218,10 +214,11 @@ frontend_tile_kernel(const FrontP p, int TT, int tiles, int smin, int smax, cons
 #pragma unroll
       for (int i = 0; i < VEC; ++i) v[i] = 0.f;
       if (ts >= 0 && ts < Tf) {
-        const float* src = src0 + ts * fold * F;
+        const int u = u0 + ts * fold * (F >> 2);
 #pragma unroll
         for (int i = 0; i < VEC; i += 4) {
-          const float4 q = *reinterpret_cast<const float4*>(src + i);
+          const int ui = u + (i >> 2);
+          const float4 q = tile4[ui ^ ((ui >> 3) & 1)];
           v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
         }
       }
@@ -272,7 +269,8 @@ extern "C" int pka_frontend_fwd(const float* feats, const int32_t* lengths, void
     for (int i = 1; i < n_ctx; ++i) { smin = ctx_host[i] < smin ? ctx_host[i] : smin; smax = ctx_host[i] > smax ? ctx_host[i] : smax; }
     const int Tf = T / fold;
     int TT = 64;
-    auto smem_of = [&](int tt) { return ((long long)(tt + smax - smin) * fold * F + (cmvn_mode ? 2 * F : 0)) * 4; };
+    // (the unit swap may touch the unit after the last one: round the tile up to a whole 128-byte bank row)
+    auto smem_of = [&](int tt) { return (((long long)(tt + smax - smin) * fold * F + 31) / 32 * 32 + (cmvn_mode ? (2 * F + 31) / 32 * 32 : 0)) * 4; };
     while (TT > 8 && smem_of(TT) > 48 * 1024) TT >>= 1;
     const long long tiles = (Tf + TT - 1) / TT;
     if (smem_of(TT) <= 48 * 1024 && (long long)B * tiles < (1LL << 31)) {
