@@ -54,8 +54,9 @@ constexpr uint32_t kIdescO = make_idesc(AT_BM, AT_D, false, true);      // O = P
 
 // Chunks of 32 keys whose keys are all allowed (the common case away from the band edge and the padded tail) skip the
 // per-element mask tests; the tile maximum is taken on the raw scores and scaled once (monotone for scale > 0).
-// FAST (PKA_ATTN_FAST=1): single pass over the scores (all 128 of a row in registers); default: two tensor-memory passes.
-template <bool FAST>
+// Two tensor-memory passes over the scores of a tile (maximum, then exponentials).  A single-pass instantiation that kept
+// all 128 scores of a row in registers was measured and removed (round 2: 106 us vs 73 us at B=4, H=8, T=1600 -- 128 more
+// live registers per thread cost more than the second tcgen05.ld pass saves).
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const AttnTcP p) {
@@ -180,21 +181,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(smem_u32(&bars[5]), j & 1);        // S_j complete -- and with it every earlier MMA (P_{j-1} V_{j-1} included)
       tc_fence_after();
-      // FAST: the whole score row of the tile stays in registers (four loads in flight, one wait, one pass);
-      // otherwise the maximum is taken chunk by chunk and the scores are loaded again for the exponentials (fewer
-      // live registers, twice the tensor-memory reads)
-      uint32_t sv[4][32];
+      // the maximum is taken chunk by chunk and the scores are loaded again for the exponentials (few live registers,
+      // twice the tensor-memory reads)
+      uint32_t sv[1][32];
       float t_max = -CUDART_INF_F;
-      if (FAST) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tmem_S + lane_addr + (uint32_t)(c * 32), sv[c]);
-        tmem_ld_wait();
-      }
       // tile maximum on the raw scores (scaled once: x -> x * c is monotone for c > 0)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (!FAST) tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
-        const uint32_t (&x)[32] = FAST ? sv[c] : sv[0];
+        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
+        const uint32_t (&x)[32] = sv[0];
         if (allow[c] == 0xffffffffu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) t_max = fmaxf(t_max, __uint_as_float(x[e]));
@@ -228,8 +223,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float pv[32];
-        if (!FAST) tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
-        const uint32_t (&x)[32] = FAST ? sv[c] : sv[0];
+        tmem_ld32(tmem_S + lane_addr + (uint32_t)(c * 32), sv[0]);
+        const uint32_t (&x)[32] = sv[0];
         if (allow[c] == 0xffffffffu) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -323,13 +318,9 @@ extern "C" int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void
   PKA_REQUIRE(out_dtype == PKA_BF16 || out_dtype == PKA_F32, PKA_EUNSUPPORTED, "attn_tc_fwd: out dtype %d", out_dtype);
   PKA_REQUIRE((out_dtype == PKA_BF16 ? d->ldo % 8 : d->ldo % 4) == 0 && aligned16(out), PKA_EALIGN, "attn_tc_fwd: out must be 16-byte aligned rows");
   static bool attr_set = false;
-  static bool fast = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     PKA_REQUIRE(e == cudaSuccess, PKA_ELAUNCH, "attn_tc_fwd: cannot opt in to %d bytes of shared memory: %s", AT_SMEM, cudaGetErrorString(e));
-    const char* env = getenv("PKA_ATTN_FAST");
-    fast = env && env[0] == '1' && d->scale > 0.f;
     attr_set = true;
   }
   CUtensorMap mapQ, mapK, mapV;
@@ -347,10 +338,7 @@ extern "C" int pka_attn_tc_fwd(const pka_attn_desc* d, const void* q, const void
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = out; p.lse = lse; p.kmask = key_mask; p.drop = d->drop;
   dim3 grid((d->Lq + AT_BM - 1) / AT_BM, d->H, d->B);
-  if (fast && d->scale > 0.f)
-    launch_k(attn_tc_fwd_kernel<true>, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
-  else
-    launch_k(attn_tc_fwd_kernel<false>, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
+  launch_k(attn_tc_fwd_kernel, grid, AT_THREADS, AT_SMEM, as_stream(stream), mapQ, mapK, mapV, p);
   return check_launch("attn_tc_fwd");
 }
 

@@ -1,5 +1,5 @@
 """Times the tensor-core attention kernels alone (CUDA-graph timed, like bench.py's probes) at the config-5 encoder shape
-and at the TIMIT decoder shapes.  usage: python tools/bench_attn.py  (PKA_ATTN_FAST=1 selects the single-pass softmax)"""
+and at the TIMIT decoder shapes.  usage: python tools/bench_attn.py"""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -35,7 +35,6 @@ def run(name, B, H, Lq, Lk, band, p_drop, d_model):
     print("%-34s fwd %8.2f us %7.1f TFLOP/s (%.1f%% of burst) | bwd(dQ + dK/dV) %8.2f us %7.1f TFLOP/s"
           % (name, tf * 1e6, fl / tf / 1e12, 100 * fl / tf / 1e12 / peaks()["bf16_tflops"], tb * 1e6, 2.5 * fl / tb / 1e12), flush=True)
 
-print("PKA_ATTN_FAST =", os.environ.get("PKA_ATTN_FAST", "0"))
 run("cfg5 enc full  B4 H8 T1600", 4, 8, 1600, 1600, None, 0.0, 512)
 run("cfg5 enc full  B4 H8 T1600 p=.1", 4, 8, 1600, 1600, None, 0.1, 512)
 run("cfg5 enc band(-100,0)", 4, 8, 1600, 1600, (-100, 0), 0.1, 512)
