@@ -69,7 +69,11 @@ class GradAllReduce:
         self.pending = list(self.expected)
         self.overlap = overlap and self.world > 1
         self.is_cuda = optimizer.flat_grad.is_cuda
-        self.comm_stream = torch.cuda.Stream() if (self.is_cuda and self.overlap) else None
+        # PKA_COMM_PRIO=-1 puts the collectives on a high-priority stream (the priority is captured with the kernel nodes
+        # of the step graph).  Measured at 2 GPUs (round 2, profiles/r02m_dp_exchange_n2.md): no difference, 1.010 vs
+        # 1.014 ms per step -- the exposed cost is the last bucket's latency, not SM starvation -- so the default stays 0.
+        prio = int(os.environ.get("PKA_COMM_PRIO", "0"))
+        self.comm_stream = torch.cuda.Stream(priority=prio) if (self.is_cuda and self.overlap) else None
         self.launched = [False] * len(self.bounds)
         self.handles = []
         self.enabled = True
