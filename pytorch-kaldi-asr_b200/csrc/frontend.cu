@@ -14,7 +14,7 @@ namespace pka {
 // One CTA per utterance.  The real frames of an utterance are one contiguous [n*F] run: a multiple of F/4 threads
 // streams it as float4 (fully coalesced) and every thread keeps hitting the SAME four features (its stride is a
 // multiple of F), so the per-feature sums live in registers (double) and meet once in shared memory, in thread order.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths, float* __restrict__ stats, int T, int F,
                   int norm_vars) {
   pdl_wait();
@@ -35,25 +35,17 @@ cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ lengths, 
         q[0] += (double)v.x * v.x; q[1] += (double)v.y * v.y; q[2] += (double)v.z * v.z; q[3] += (double)v.w * v.w;
       };
       const float4* x4 = reinterpret_cast<const float4*>(xb);
-      // Rounds of EIGHT predicated loads per thread; the first round is requested BEFORE the utterance length is known
-      // (it only has to stay inside the utterance's T*F buffer; vectors beyond the real frames are dropped afterwards), so
-      // the length load and the first data round share one trip to memory, and the remainder is one predicated round
-      // instead of a tail of single loads.  Round 2 measurements at 2048 x 450 x 40 (18 vectors per thread): 4-wide rounds
-      // + single-load tail = 6 dependent trips behind the length load, 61 % of the copy bandwidth; a software-pipelined
-      // 4+4 version kept the tail and lost a resident CTA to registers, 55 %.
-      const long long tot4 = (long long)T * F / 4;
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const long long eu = tid + (long long)u * nact; v[u] = eu < tot4 ? x4[eu] : zero4; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) if (tid + (long long)u * nact < n4) acc(v[u]);
-      for (long long e = tid + 8LL * nact; e < n4; e += 8LL * nact) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const long long eu = e + (long long)u * nact; v[u] = eu < n4 ? x4[eu] : zero4; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc(v[u]);                 // (a zero vector adds exact zeros)
+      long long e = tid;
+      for (; e + 3LL * nact < n4; e += 4LL * nact) {           // four independent loads in flight per thread
+        const float4 v0 = x4[e], v1 = x4[e + nact], v2 = x4[e + 2LL * nact], v3 = x4[e + 3LL * nact];
+        acc(v0); acc(v1); acc(v2); acc(v3);
       }
+      // (round 2, both measured at 2048 utterances x 450 frames x 40 and both slower than this loop's 38 us = 59 % of the
+      //  copy bandwidth: a software-pipelined version with the next four loads requested before the accumulation -- 70
+      //  registers, 3 CTAs per SM, 42 us; rounds of eight predicated loads with a speculative first round issued before
+      //  the length is known -- 80 registers with spills, 53 us.  What is left is the serial part of every short CTA
+      //  (length load, 4-5 dependent load rounds, the fixed-order double-precision finish) and the 3.5-wave tail.)
+      for (; e < n4; e += nact) acc(x4[e]);
     } else {
       for (long long e = tid; e < (long long)n * F; e += nact) { const double v = xb[e]; s[0] += v; q[0] += v * v; }
     }
