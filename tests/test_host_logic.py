@@ -187,3 +187,38 @@ def test_gradient_allreduce_is_a_sum_over_ranks_world2_gloo(overlap):
     assert torch.allclose(g0[off[1]:off[1] + 3], torch.full((3,), 4.0))      # 2 + 2, NOT averaged
     assert torch.allclose(g0[off[3]:off[3] + 11], torch.full((11,), 7.0))    # (0+3) + (1+3)
     assert s0.tolist() == [3.0, 4.0, 6.0] and s1.tolist() == s0.tolist()
+
+
+def test_no_cache_decoder_reads_prefixes_off_the_lattice_arrays():
+    """decode.BeamDecoder._slot_prefixes (the no-cache path of a non-causal decoder band): token prefixes of the live beam
+    slots walked along the back-pointers of the device lattice arrays.  Host-side index logic, checked on CPU tensors
+    against the oracle lattice (T/Lattice.py:84-107) advanced with random scores; idle slots give all-BOS rows."""
+    from oracle.lattice import BeamLattice
+    from pytorch_kaldi_asr_b200.decode import BeamDecoder
+    rng = np.random.RandomState(7)
+    beam, V, max_len, n_utt = 4, 9, 6, 3
+    lats = [BeamLattice(max_len, beam) for _ in range(n_utt)]
+    for step in range(4):
+        E = 1 + beam * max_len
+        prev = torch.full((n_utt, E), -1, dtype=torch.int32)
+        word = torch.zeros((n_utt, E), dtype=torch.int32)
+        slot_edge = torch.zeros((n_utt, beam), dtype=torch.int32)
+        for u, lat in enumerate(lats):
+            prev[u, :len(lat.prev)] = torch.tensor(lat.prev, dtype=torch.int32)
+            word[u, :len(lat.word)] = torch.tensor(lat.word, dtype=torch.int32)
+            live = lat.active()
+            slot_edge[u, :len(live)] = torch.tensor(live, dtype=torch.int32)
+        bd = BeamDecoder.__new__(BeamDecoder)                      # index logic only: no model, no device
+        bd.n_utt, bd.beam, bd.dev = n_utt, beam, "cpu"
+        bd.slot_edge, bd.edge_prev, bd.edge_word = slot_edge, prev, word
+        toks = bd._slot_prefixes(step + 1).view(n_utt, beam, step + 1)
+        for u, lat in enumerate(lats):
+            seqs, _ = lat.get_results("active")
+            for k, seq in enumerate(seqs):
+                assert toks[u, k].tolist() == seq
+            for k in range(len(seqs), beam):
+                assert toks[u, k].tolist() == [constants.BOS] * (step + 1)
+        for lat in lats:                                           # next step: random scores, EOS made unlikely
+            lp = rng.randn(max(1, lat.num_curr_active), V).astype(np.float32)
+            lp[:, constants.EOS] -= 3.0
+            lat.advance(lp)
