@@ -87,3 +87,21 @@ def test_product_package_never_imports_the_oracle():
             if name.endswith(".py") and pattern.search(open(os.path.join(base, name), encoding="utf-8").read()):
                 offenders.append(os.path.relpath(os.path.join(base, name), ROOT))
     assert offenders == []
+
+
+def test_layernorm_backward_partial_row_contract_is_host_arithmetic(library):
+    """pka_ln_bwd_blocks(rows) is pure host code (no device call): it is both the grid of the LayerNorm backward kernel and
+    the number of partial rows the caller sizes its workspace / reduction job with (include/pka_b200.h).  Small tensors:
+    one row per warp, at most 256 partial rows; large ones: a persistent grid that is a whole number of waves for 3, 2 and
+    1 resident CTAs per SM (148 * 6), mid-sized ones one CTA pair per SM (148 * 2)."""
+    lib = ctypes.CDLL(library.LIB_PATH)
+    lib.pka_ln_bwd_blocks.restype = ctypes.c_int
+    lib.pka_ln_bwd_blocks.argtypes = [ctypes.c_int]
+    f = lib.pka_ln_bwd_blocks
+    assert f(1) == 1 and f(8) == 1 and f(9) == 2
+    assert f(2016) == 252                      # the timed step's decoder rows: one row per warp, 8 warps per CTA
+    assert f(8192) == 256 and f(4096) == 256
+    assert f(8193) == 296 and f(12792) == 296  # config 5's encoder rows
+    assert f(148 * 6 * 8 * 4) == 888 and f(223552) == 888
+    for rows in (1, 7, 2016, 8192, 8193, 30000, 1 << 20):
+        assert 1 <= f(rows) <= 888
